@@ -1,0 +1,72 @@
+"""ctypes binding of libnpore_b200.so (include/npore_b200.h).  No CPU fallback: if the CUDA library is
+missing, importing this module's `lib()` raises."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnpore_b200.so")
+
+NPORE_OUT_STANDARDIZE = 1
+NPORE_OUT_RLE = 2
+NPORE_OUT_NO_EXPANDED = 4
+ST_BAD_CIGAR = 16
+
+
+class Batch(C.Structure):
+    _fields_ = [("n_items", C.c_int32),
+                ("ref_codes", C.c_void_p), ("ref_start", C.c_void_p), ("ref_len", C.c_void_p), ("ref_total", C.c_int64),
+                ("seq_codes", C.c_void_p), ("seq_start", C.c_void_p), ("seq_len", C.c_void_p), ("seq_total", C.c_int64),
+                ("cigar_rle", C.c_void_p), ("cigar_off", C.c_void_p)]
+
+
+class Result(C.Structure):
+    _fields_ = [("ops", C.c_void_p), ("ops_capacity", C.c_int64), ("ops_off", C.c_void_p),
+                ("rle", C.c_void_p), ("rle_capacity", C.c_int64), ("rle_off", C.c_void_p),
+                ("chunk_scores", C.c_void_p), ("score_capacity", C.c_int64), ("score_off", C.c_void_p),
+                ("status", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_items", C.c_int64), ("n_chunks", C.c_int64), ("n_cu", C.c_int64),
+                ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("tb_bytes", C.c_int64),
+                ("ms_plan", C.c_float), ("ms_annotate", C.c_float), ("ms_forward", C.c_float),
+                ("ms_traceback", C.c_float), ("ms_finish", C.c_float), ("ms_kernels_total", C.c_float),
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
+                ("launches", C.c_int32), ("n_sub_batches", C.c_int32), ("overflow_runs", C.c_int32), ("sm_count", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_count_chunks", "npore_upload", "npore_run", "npore_download",
+           "npore_align_batch", "npore_get_np_info", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is not built (python -c 'import __graft_entry__ as g; g.build()'); "
+                               "npore_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.npore_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_float, C.c_float, C.c_int, C.c_int]
+        L.npore_ctx_destroy.argtypes = [C.c_void_p]
+        L.npore_ctx_destroy.restype = None
+        L.npore_count_chunks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        L.npore_count_chunks.restype = C.c_int64
+        L.npore_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
+        L.npore_run.argtypes = [C.c_void_p, C.c_uint32]
+        L.npore_download.argtypes = [C.c_void_p, C.POINTER(Result)]
+        L.npore_align_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_uint32, C.POINTER(Result)]
+        L.npore_get_np_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.npore_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.npore_strerror.argtypes = [C.c_int]
+        L.npore_strerror.restype = C.c_char_p
+        L.npore_last_error.argtypes = [C.c_void_p]
+        L.npore_last_error.restype = C.c_char_p
+        L.npore_version.restype = C.c_char_p
+        _lib = L
+    return _lib

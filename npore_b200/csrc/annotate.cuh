@@ -1,0 +1,183 @@
+// annotate.cuh -- get_np_info on device (reference: src/aln.pyx:179-251), per chunk slice (aln.pyx:453-456),
+// emitting the packed per-position records the forward kernel consumes.  Dataflow validated on the CPU by
+// oracle/pull_model.c:pm_np_raw / relay_col / relay_row (same statements).
+//
+// The reference scans positions sequentially with "don't overwrite" rules (aln.pyx:238-249).  Equivalent
+// parallel form, for n = 1..max_n in order (the `longest` test of period n reads final L of periods < n):
+//   e[q]   = (q+n < len && s[q]==s[q+n])
+//   runs   = maximal stretches of e==true plus their terminating false position; nf[q] / lf[q] = next / last
+//            false position (two tile scans)
+//   chains = positions of one run congruent mod n.  One walker per chain head visits its chain in ascending
+//            order carrying (first active writer, last active writer with l > max_l) -- that is all the
+//            sequential overwrite rules can depend on (incl. the max_l clamp quirk).
+// raw[p][n-1] = L | 0x80 if L_IDX == 0.
+//
+// Records (one per slice position, "relaid" so that the record at column j holds what cell (.,j) gathers):
+//   colrec[j] (uint2):  .x = raw[j-n][n] for n=1..4 (one byte each);
+//                       .y = raw[j-5][5] | raw[j-6][6]<<8 | SHRmask<<16 | LENmask<<22 | base(ref[j-1])<<28
+//                       SHRmask bit n-1 = (raw[j-n][n] & 0x7f) != 0 ; LENmask bit n-1 = raw[j][n] has L!=0 && L_IDX==0
+//   rowrec[i] (uint32): bits 0-5  = (raw_seq[i-n][n] & 0x7f) != 0 ; bits 8-13 = L_IDX(seq)[i-n][n]==0 ; bits 16-18 = seq[i-1]
+#pragma once
+#include "common.cuh"
+
+#define ANN_THREADS 256
+
+struct AnnotateArgs {
+    const ChunkDesc *chunks;
+    const ChunkSlot *slots;        // indexed like `order`
+    const int32_t *order;          // chunk ids of this sub-batch
+    int n;                         // chunks in this sub-batch
+    const ItemDesc *items;
+    const uint8_t *ref_codes, *seq_codes;
+    uint8_t *raw_ref, *raw_seq;    // 8 B per entry
+    int32_t *nf_ref, *lf_ref, *nf_seq, *lf_seq;
+    uint2 *colrec; uint32_t *rowrec;
+    int max_n, max_l;
+};
+
+// np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
+__device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n, int max_l,
+                               uint8_t *raw, int32_t *nf, int32_t *lf, int32_t *full_out)
+{
+    __shared__ int s_ff[ANN_THREADS], s_lfp[ANN_THREADS];
+    const int tid = threadIdx.x;
+    for (int q = tid; q < len; q += ANN_THREADS) reinterpret_cast<uint2 *>(raw)[q] = make_uint2(0u, 0u);
+    if (full_out) for (int q = tid; q < len * 2 * max_n; q += ANN_THREADS) full_out[q] = 0;
+    const int T = (len + ANN_THREADS - 1) / ANN_THREADS;
+    const int t0 = min(len, tid * T), t1 = min(len, t0 + T);
+    __syncthreads();
+
+    for (int n = 1; n <= max_n; n++) {
+        // ---- tile summaries: first / last false position of e[] in my tile
+        int ff = 0x7fffffff, lfp = -1;
+        for (int q = t0; q < t1; q++) {
+            const bool e = (q + n < len) && (s[q] == s[q + n]);
+            if (!e) { if (ff == 0x7fffffff) ff = q; lfp = q; }
+        }
+        s_ff[tid] = ff; s_lfp[tid] = lfp;
+        __syncthreads();
+        // suffix-min of ff over later tiles, prefix-max of lfp over earlier tiles (Hillis-Steele)
+        for (int o = 1; o < ANN_THREADS; o <<= 1) {
+            int a = s_ff[tid], b = s_lfp[tid];
+            if (tid + o < ANN_THREADS) a = min(a, s_ff[tid + o]);
+            if (tid >= o) b = max(b, s_lfp[tid - o]);
+            __syncthreads();
+            s_ff[tid] = a; s_lfp[tid] = b;
+            __syncthreads();
+        }
+        int nxt = (tid + 1 < ANN_THREADS) ? s_ff[tid + 1] : 0x7fffffff;   // first false after my tile
+        int prv = tid ? s_lfp[tid - 1] : -1;                              // last false before my tile
+        if (nxt == 0x7fffffff) nxt = len;
+        for (int q = t1 - 1; q >= t0; q--) {
+            const bool e = (q + n < len) && (s[q] == s[q + n]);
+            if (!e) nxt = q;
+            nf[q] = nxt;
+        }
+        for (int q = t0; q < t1; q++) {
+            lf[q] = prv;
+            const bool e = (q + n < len) && (s[q] == s[q + n]);
+            if (!e) prv = q;
+        }
+        __syncthreads();
+        // ---- one walker per chain head
+        for (int h = tid; h < len; h += ANN_THREADS) {
+            const int rs = lf[h] + 1;
+            if (h - rs >= n) continue;
+            const int end = nf[rs];
+            int first = -1, lfirst = 0, zlast = -1;
+            for (int p = h; p <= end; p += n) {
+                const int m = end - p;
+                int l = m / n; if (l > 0) l++;
+                bool act = s[p] != 0 && l > 2;
+                if (act) {
+                    const uint2 rw = reinterpret_cast<const uint2 *>(raw)[p];
+                    for (int n2 = 1; n2 < n; n2++) {
+                        const uint32_t b = ((n2 <= 4 ? rw.x >> (8 * (n2 - 1)) : rw.y >> (8 * (n2 - 5))) & 0x7fu);
+                        if (l * n <= (int)b * n2) act = false;
+                    }
+                }
+                if (act) {
+                    if (first < 0) { first = p; lfirst = l; }
+                    if (l > max_l) zlast = p;
+                }
+                if (first >= 0) {
+                    int L, X;
+                    if (zlast >= 0) { L = max_l; X = (p - zlast) / n; }
+                    else { L = min(lfirst, max_l); X = (p - first) / n; }
+                    raw[(size_t)p * 8 + n - 1] = (uint8_t)(L | (X == 0 ? 0x80 : 0));
+                    if (full_out) {
+                        full_out[((size_t)p * 2 + 0) * max_n + n - 1] = L;
+                        full_out[((size_t)p * 2 + 1) * max_n + n - 1] = X;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__device__ __forceinline__ uint32_t raw_byte(const uint8_t *raw, int len, int p, int n)
+{
+    return (p >= 0 && p < len) ? (uint32_t)raw[(size_t)p * 8 + n - 1] : 0u;
+}
+
+__global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
+{
+    const int ci = blockIdx.x >> 1, side = blockIdx.x & 1;
+    if (ci >= a.n) return;
+    const ChunkDesc c = a.chunks[a.order[ci]];
+    const ChunkSlot sl = a.slots[ci];
+    if (!c.valid) return;
+    const ItemDesc &I = a.items[c.item];
+    if (side == 0) {
+        const int len = c.rlen;
+        const uint8_t *s = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
+        uint8_t *raw = a.raw_ref + sl.col_off * 8;
+        annotate_slice(s, len, a.max_n, a.max_l, raw, a.nf_ref + sl.col_off, a.lf_ref + sl.col_off, nullptr);
+        uint2 *out = a.colrec + sl.col_off;
+        for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
+            uint2 v = make_uint2(0u, 0u);
+            if (j < len + 8) {
+                uint32_t shr = 0, lenm = 0;
+#pragma unroll
+                for (int n = 1; n <= NP_MAXN; n++) {
+                    const uint32_t b = raw_byte(raw, len, j - n, n);
+                    if (n <= 4) v.x |= b << (8 * (n - 1)); else v.y |= b << (8 * (n - 5));
+                    if (b & 0x7fu) shr |= 1u << (n - 1);
+                    const uint32_t o = raw_byte(raw, len, j, n);
+                    if ((o & 0x7fu) && (o & 0x80u)) lenm |= 1u << (n - 1);
+                }
+                const uint32_t base = (j >= 1 && j - 1 < len) ? s[j - 1] : 0u;
+                v.y |= shr << 16 | lenm << 22 | (base & 7u) << 28;
+            }
+            out[j] = v;
+        }
+    } else {
+        const int len = c.slen;
+        const uint8_t *s = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
+        uint8_t *raw = a.raw_seq + sl.row_off * 8;
+        annotate_slice(s, len, a.max_n, a.max_l, raw, a.nf_seq + sl.row_off, a.lf_seq + sl.row_off, nullptr);
+        uint32_t *out = a.rowrec + sl.row_off;
+        for (int i = threadIdx.x; i < sl.row_cap; i += ANN_THREADS) {
+            uint32_t v = 0;
+            if (i < len + 8) {
+#pragma unroll
+                for (int n = 1; n <= NP_MAXN; n++) {
+                    const uint32_t b = raw_byte(raw, len, i - n, n);
+                    if (b & 0x7fu) v |= 1u << (n - 1);
+                    if (b & 0x80u) v |= 1u << (8 + n - 1);
+                }
+                const uint32_t base = (i >= 1 && i - 1 < len) ? s[i - 1] : 0u;
+                v |= (base & 7u) << 16;
+            }
+            out[i] = v;
+        }
+    }
+}
+
+// src/aln.pyx:179-251 as a stand-alone device entry (npore_get_np_info): one CTA, one sequence.
+__global__ void __launch_bounds__(ANN_THREADS)
+np_info_kernel(const uint8_t *s, int len, int max_n, int max_l, uint8_t *raw, int32_t *nf, int32_t *lf, int32_t *out)
+{
+    annotate_slice(s, len, max_n, max_l, raw, nf, lf, out);
+}

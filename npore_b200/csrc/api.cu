@@ -1,0 +1,563 @@
+// api.cu -- C ABI of libnpore_b200.so (include/npore_b200.h) and the host side of the GPU batch scheduler that
+// replaces the reference's multiprocessing.Pool fan-out (src/realign.py:110-114, src/standardize_vcf.py:30-31).
+//
+// Pipeline of one batch (all on one stream of one B200):
+//   upload   : items / base codes / RLE CIGARs -> HBM
+//   run      : plan_kernel      (aln.pyx:386-392  D/I bit string, rank arrays, chunk descriptors)
+//              per sub-batch of chunks, largest first (scratch bounded by the memory budget):
+//                annotate_kernel  (aln.pyx:179-251  np-info records of both slices of every chunk)
+//                forward_kernel   (aln.pyx:465-667  the recurrence; persistent warps, one chunk per warp)
+//                traceback_kernel (aln.pyx:671-742)
+//              gather / standardize / rle kernels (aln.pyx:742, bam.pyx:65-78, cig.pyx:13-38)
+//   download : per-item op strings, run-length words, chunk scores, status -> host
+// There is no CPU fallback: every entry point fails with NPORE_ERR_NO_DEVICE / NPORE_ERR_CUDA without a GPU.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/npore_b200.h"
+#include "common.cuh"
+#include "plan.cuh"
+#include "annotate.cuh"
+#include "forward.cuh"
+#include "traceback.cuh"
+#include "finish.cuh"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {      // pinned staging owned by the library (download path)
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes + bytes / 8 + 256);
+        if (e == cudaSuccess) cap = bytes + bytes / 8 + 256;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct SubBatch { int first, count; };
+
+}  // namespace
+
+struct npore_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    AlignParams P{};
+    int cpl = 2, tbs = 2, np_n = 0;
+    size_t scratch_budget = 0;
+    DevBuf d_sub, d_np;
+    // batch-resident
+    DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
+        d_item_len, d_item_status, d_rle_out, d_rle_len, d_order, d_slots, d_counter, d_ovf, d_ovf_count;
+    // per sub-batch scratch
+    DevBuf d_colrec, d_rowrec, d_raw_ref, d_raw_seq, d_nf_ref, d_lf_ref, d_nf_seq, d_lf_seq, d_tb;
+    HostBuf h_ops, h_rle, h_small;
+    std::vector<ItemDesc> items;
+    std::vector<int32_t> order;
+    std::vector<int32_t> chunk_bmax;
+    std::vector<ChunkSlot> slots;
+    std::vector<SubBatch> subs;
+    int64_t n_chunks = 0, total_ops = 0, total_rle = 0, total_words = 0;
+    bool uploaded = false, ran = false;
+    uint32_t run_flags = 0;
+    npore_stats stats{};
+    cudaEvent_t ev[8]{};
+    std::string err;
+    static const int OVF_CAP = 1 << 16;
+};
+
+namespace {
+
+int fail(npore_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) { c->err += ": "; c->err += cudaGetErrorString(e); }
+    }
+    cudaGetLastError();
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? NPORE_ERR_OOM : NPORE_ERR_CUDA, #call, e_); \
+    } while (0)
+
+inline int chunks_of(int total, int max_b_rows)
+{
+    const int step = max_b_rows - 1;
+    return total > 0 ? (total + step - 1) / step : 0;
+}
+
+template <int CPL>
+int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
+{
+    const size_t smem = (size_t)FWD_WARPS * 4 * NP_RING * 32 * CPL * sizeof(float);
+    CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, FWD_WARPS * 32, smem));
+    if (per_sm < 1) per_sm = 1;
+    int grid = std::min((n_sub + FWD_WARPS - 1) / FWD_WARPS, ctx->sm_count * per_sm);
+    if (grid < 1) grid = 1;
+    forward_kernel<CPL><<<grid, FWD_WARPS * 32, smem, ctx->stream>>>(fa);
+    CU(cudaGetLastError());
+    return NPORE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *npore_version(void) { return "npore_b200 0.1.0 (sm_100a)"; }
+
+const char *npore_strerror(int code)
+{
+    switch (code) {
+    case NPORE_OK: return "ok";
+    case NPORE_ERR_BAD_ARG: return "bad argument";
+    case NPORE_ERR_CUDA: return "CUDA error";
+    case NPORE_ERR_OOM: return "out of device memory";
+    case NPORE_ERR_NO_DEVICE: return "no CUDA device";
+    case NPORE_ERR_STATE: return "call out of order (upload -> run -> download)";
+    case NPORE_ERR_CAPACITY: return "caller buffer too small";
+    default: return "unknown error";
+    }
+}
+
+const char *npore_last_error(const npore_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const float *np_scores, int np_n,
+                     int np_dim, int max_n, int max_l, float indel_start, float indel_extend, int max_b_rows, int r)
+{
+    if (!out) return NPORE_ERR_BAD_ARG;
+    *out = nullptr;
+    if (!sub_scores || !np_scores) return NPORE_ERR_BAD_ARG;
+    if (max_n < 0 || max_n > NP_MAXN || max_n > np_n) return NPORE_ERR_BAD_ARG;
+    if (max_l < 1 || max_l > 127 || np_dim < max_l) return NPORE_ERR_BAD_ARG;   // L must fit 7 bits; index clamp is max_l-1
+    if (max_b_rows < 2 || max_b_rows > 65000) return NPORE_ERR_BAD_ARG;          // runs are carried in 16 bits
+    if (r < 1 || 2 * r + 1 > 32 * 8) return NPORE_ERR_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return NPORE_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) return NPORE_ERR_BAD_ARG;
+    npore_ctx *ctx = new npore_ctx();
+    ctx->device = device;
+    auto bail = [&](int code) { npore_ctx_destroy(ctx); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(NPORE_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(NPORE_ERR_CUDA);
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(NPORE_ERR_CUDA);
+    for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(NPORE_ERR_CUDA);
+    ctx->P.r = r; ctx->P.W = 2 * r + 1; ctx->P.max_n = max_n; ctx->P.max_l = max_l; ctx->P.max_b_rows = max_b_rows;
+    ctx->P.np_dim = np_dim; ctx->P.np_clamp = max_l - 1;
+    ctx->P.gap_open = indel_start; ctx->P.gap_ext = indel_extend;
+    ctx->np_n = np_n;
+    const int W = 2 * r + 1;
+    ctx->cpl = W <= 32 ? 1 : W <= 64 ? 2 : W <= 128 ? 4 : 8;
+    ctx->tbs = np_tbs(ctx->cpl);
+    if (ctx->d_sub.ensure(25 * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
+    if (ctx->d_np.ensure((size_t)np_n * np_dim * np_dim * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
+    if (cudaMemcpy(ctx->d_sub.p, sub_scores, 25 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NPORE_ERR_CUDA);
+    if (cudaMemcpy(ctx->d_np.p, np_scores, (size_t)np_n * np_dim * np_dim * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(NPORE_ERR_CUDA);
+    if (ctx->d_counter.ensure(64) != cudaSuccess || ctx->d_ovf_count.ensure(64) != cudaSuccess ||
+        ctx->d_ovf.ensure(sizeof(OverflowRec) * npore_ctx::OVF_CAP) != cudaSuccess) return bail(NPORE_ERR_OOM);
+    size_t fr = 0, tot = 0;
+    cudaMemGetInfo(&fr, &tot);
+    ctx->scratch_budget = (size_t)((double)fr * 0.55);
+    if (const char *s = getenv("NPORE_SCRATCH_MB")) ctx->scratch_budget = (size_t)atoll(s) << 20;
+    *out = ctx;
+    return NPORE_OK;
+}
+
+void npore_ctx_destroy(npore_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
+                      &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
+                      &ctx->d_item_status, &ctx->d_rle_out, &ctx->d_rle_len, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
+                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq,
+                      &ctx->d_nf_ref, &ctx->d_lf_ref, &ctx->d_nf_seq, &ctx->d_lf_seq, &ctx->d_tb};
+    for (auto *b : bufs) b->release();
+    ctx->h_ops.release(); ctx->h_rle.release(); ctx->h_small.release();
+    for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int64_t npore_count_chunks(const npore_ctx *ctx, int32_t n_items, const int32_t *ref_len, const int32_t *seq_len)
+{
+    if (!ctx || n_items < 0 || (n_items && (!ref_len || !seq_len))) return NPORE_ERR_BAD_ARG;
+    int64_t n = 0;
+    for (int i = 0; i < n_items; i++) n += chunks_of(ref_len[i] + seq_len[i], ctx->P.max_b_rows);
+    return n;
+}
+
+int npore_upload(npore_ctx *ctx, const npore_batch *b)
+{
+    if (!ctx || !b || b->n_items < 0) return NPORE_ERR_BAD_ARG;
+    const int n = b->n_items;
+    if (n && (!b->ref_start || !b->ref_len || !b->seq_start || !b->seq_len || !b->cigar_off)) return fail(ctx, NPORE_ERR_BAD_ARG, "null batch array");
+    CU(cudaSetDevice(ctx->device));
+    ctx->uploaded = ctx->ran = false;
+    ctx->items.assign(n, ItemDesc{});
+    int64_t out_off = 0, words = 0, nchunks = 0, n_cu = 0;
+    for (int i = 0; i < n; i++) {
+        ItemDesc &I = ctx->items[i];
+        const int64_t rl = b->ref_len[i], sl = b->seq_len[i];
+        if (rl < 0 || sl < 0 || rl + sl > 0x7ffffff0ll) return fail(ctx, NPORE_ERR_BAD_ARG, "item too long");
+        if (b->ref_start[i] < 0 || b->ref_start[i] + rl > b->ref_total || b->seq_start[i] < 0 || b->seq_start[i] + sl > b->seq_total)
+            return fail(ctx, NPORE_ERR_BAD_ARG, "sequence range outside buffer");
+        const int64_t cn = b->cigar_off[i + 1] - b->cigar_off[i];
+        if (cn < 0 || cn > 0x7ffffff0ll) return fail(ctx, NPORE_ERR_BAD_ARG, "bad cigar_off");
+        I.ref_start = b->ref_start[i]; I.seq_start = b->seq_start[i];
+        I.ref_len = (int32_t)rl; I.seq_len = (int32_t)sl;
+        I.cig_off = b->cigar_off[i] - b->cigar_off[0]; I.cig_n = (int32_t)cn;
+        I.total_ops = (int32_t)(rl + sl);
+        I.bit_word_off = words; words += (I.total_ops >> 5) + 2;
+        I.out_off = out_off; out_off += (I.total_ops + 3) & ~3;      // keep item regions 4-byte aligned
+        I.n_chunks = chunks_of(I.total_ops, ctx->P.max_b_rows);
+        if (nchunks + I.n_chunks > 0x7ffffff0ll) return fail(ctx, NPORE_ERR_BAD_ARG, "too many chunks");
+        I.chunk_first = (int32_t)nchunks; nchunks += I.n_chunks;
+        n_cu += ((int64_t)I.total_ops + I.n_chunks) * ctx->P.W;
+        I.status = 0;
+    }
+    ctx->n_chunks = nchunks; ctx->total_ops = out_off; ctx->total_words = words;
+    ctx->total_rle = n ? b->cigar_off[n] - b->cigar_off[0] : 0;
+
+    // chunk size upper bounds (exact B needs the break shift computed on device) and processing order
+    const int step = ctx->P.max_b_rows - 1;
+    ctx->chunk_bmax.resize(nchunks);
+    ctx->order.resize(nchunks);
+    std::vector<int32_t> partial;
+    int64_t w = 0;
+    for (int i = 0; i < n; i++) {
+        const ItemDesc &I = ctx->items[i];
+        for (int k = 0; k < I.n_chunks; k++) {
+            const int cid = I.chunk_first + k;
+            const bool last = (k + 1 == I.n_chunks);
+            ctx->chunk_bmax[cid] = last ? (I.total_ops - k * step + 2) : (step + 2);
+            if (!last) ctx->order[w++] = cid; else partial.push_back(cid);
+        }
+    }
+    std::sort(partial.begin(), partial.end(), [&](int32_t x, int32_t y) {
+        return ctx->chunk_bmax[x] != ctx->chunk_bmax[y] ? ctx->chunk_bmax[x] > ctx->chunk_bmax[y] : x < y; });
+    // full chunks first unless some final chunk is longer than a full one (never: bmax(last) <= step + 2)
+    for (int32_t cid : partial) ctx->order[w++] = cid;
+
+    // device buffers
+    CU(ctx->d_items.ensure(sizeof(ItemDesc) * (size_t)std::max(n, 1)));
+    CU(ctx->d_ref.ensure((size_t)b->ref_total + 64));
+    CU(ctx->d_seq.ensure((size_t)b->seq_total + 64));
+    CU(ctx->d_rle.ensure(sizeof(uint32_t) * (size_t)(ctx->total_rle + 1)));
+    CU(ctx->d_grp.ensure(sizeof(int32_t) * (size_t)(ctx->total_rle + n + 1)));
+    CU(ctx->d_bits.ensure(sizeof(uint32_t) * (size_t)(words + 128)));
+    CU(ctx->d_cum.ensure(sizeof(uint32_t) * (size_t)(words + 128)));
+    CU(ctx->d_chunks.ensure(sizeof(ChunkDesc) * (size_t)std::max<int64_t>(nchunks, 1)));
+    CU(ctx->d_chunk_out.ensure(sizeof(ChunkOut) * (size_t)std::max<int64_t>(nchunks, 1)));
+    CU(ctx->d_order.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(nchunks, 1)));
+    CU(ctx->d_slots.ensure(sizeof(ChunkSlot) * (size_t)std::max<int64_t>(nchunks, 1)));
+    CU(ctx->d_scratch_ops.ensure((size_t)out_off + 64));
+    CU(ctx->d_ops.ensure((size_t)out_off + 64));
+    CU(ctx->d_item_len.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+    CU(ctx->d_item_status.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+    CU(ctx->d_rle_len.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (n) CU(cudaMemcpyAsync(ctx->d_items.p, ctx->items.data(), sizeof(ItemDesc) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (b->ref_total) CU(cudaMemcpyAsync(ctx->d_ref.p, b->ref_codes, (size_t)b->ref_total, cudaMemcpyHostToDevice, ctx->stream));
+    if (b->seq_total) CU(cudaMemcpyAsync(ctx->d_seq.p, b->seq_codes, (size_t)b->seq_total, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->total_rle)
+        CU(cudaMemcpyAsync(ctx->d_rle.p, b->cigar_rle + b->cigar_off[0], sizeof(uint32_t) * (size_t)ctx->total_rle, cudaMemcpyHostToDevice, ctx->stream));
+    if (nchunks) CU(cudaMemcpyAsync(ctx->d_order.p, ctx->order.data(), sizeof(int32_t) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    npore_stats &S = ctx->stats;
+    S = npore_stats{};
+    S.n_items = n; S.n_chunks = nchunks; S.n_cu = n_cu; S.sm_count = ctx->sm_count;
+    S.h2d_bytes = (int64_t)sizeof(ItemDesc) * n + b->ref_total + b->seq_total + 4 * ctx->total_rle + 4 * nchunks;
+    cudaEventElapsedTime(&S.ms_h2d, ctx->ev[0], ctx->ev[1]);
+    ctx->uploaded = true;
+    return NPORE_OK;
+}
+
+int npore_run(npore_ctx *ctx, uint32_t flags)
+{
+    if (!ctx) return NPORE_ERR_BAD_ARG;
+    if (!ctx->uploaded) return fail(ctx, NPORE_ERR_STATE, "npore_run before npore_upload");
+    if ((flags & NPORE_OUT_NO_EXPANDED) && !(flags & NPORE_OUT_RLE)) return fail(ctx, NPORE_ERR_BAD_ARG, "NO_EXPANDED needs RLE");
+    CU(cudaSetDevice(ctx->device));
+    const int n = (int)ctx->items.size();
+    const int64_t nchunks = ctx->n_chunks;
+    const int NC = 32 * ctx->cpl;
+    npore_stats &S = ctx->stats;
+    S.launches = 0; S.tb_bytes = 0;
+    ctx->run_flags = flags;
+    if (flags & NPORE_OUT_RLE) CU(ctx->d_rle_out.ensure(sizeof(uint32_t) * (size_t)(ctx->total_ops + 64)));
+
+    // ---- sub-batches: greedy over `order` under the scratch budget (sizes from the host-side upper bounds)
+    ctx->slots.assign(nchunks, ChunkSlot{});
+    ctx->subs.clear();
+    size_t max_col = 0, max_row = 0, max_tb = 0;
+    {
+        const size_t per_entry = 8 + 8 + 4 + 4 + 4 + 8 + 4 + 4;   // colrec, raw_ref, nf/lf ref, rowrec, raw_seq, nf/lf seq
+        size_t col = 0, row = 0, tb = 0; int first = 0;
+        for (int64_t k = 0; k < nchunks; k++) {
+            const int bm = ctx->chunk_bmax[ctx->order[k]];
+            const size_t ent = (size_t)((bm + NC + 128 + 31) & ~31);
+            const size_t need = (col + ent) * per_entry + (tb + bm) * (size_t)(64 * ctx->tbs);
+            if (k > first && need > ctx->scratch_budget) {
+                ctx->subs.push_back({first, (int)(k - first)});
+                max_col = std::max(max_col, col); max_row = std::max(max_row, row); max_tb = std::max(max_tb, tb);
+                col = row = tb = 0; first = (int)k;
+            }
+            ChunkSlot &sl = ctx->slots[k];
+            sl.col_off = (int64_t)col; sl.row_off = (int64_t)row; sl.tb_off = (int64_t)tb;
+            sl.col_cap = sl.row_cap = (int32_t)ent;
+            col += ent; row += ent; tb += bm;
+        }
+        if (nchunks > first) {
+            ctx->subs.push_back({first, (int)(nchunks - first)});
+            max_col = std::max(max_col, col); max_row = std::max(max_row, row); max_tb = std::max(max_tb, tb);
+        }
+    }
+    CU(ctx->d_colrec.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
+    CU(ctx->d_nf_ref.ensure(max_col * 4 + 64)); CU(ctx->d_lf_ref.ensure(max_col * 4 + 64));
+    CU(ctx->d_rowrec.ensure(max_row * 4 + 64)); CU(ctx->d_raw_seq.ensure(max_row * 8 + 64));
+    CU(ctx->d_nf_seq.ensure(max_row * 4 + 64)); CU(ctx->d_lf_seq.ensure(max_row * 4 + 64));
+    CU(ctx->d_tb.ensure(max_tb * (size_t)(64 * ctx->tbs) + 256));
+    if (nchunks) CU(cudaMemcpyAsync(ctx->d_slots.p, ctx->slots.data(), sizeof(ChunkSlot) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_ovf_count.p, 0, 4, ctx->stream));
+
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    // ---- plan
+    if (n) {
+        plan_kernel<<<n, PLAN_THREADS, 0, ctx->stream>>>(ctx->d_items.as<ItemDesc>(), n, ctx->d_rle.as<uint32_t>(), ctx->d_grp.as<int32_t>(),
+                                                         ctx->d_bits.as<uint32_t>(), ctx->d_cum.as<uint32_t>(), ctx->d_chunks.as<ChunkDesc>(),
+                                                         ctx->P.max_b_rows);
+        CU(cudaGetLastError()); S.launches++;
+    }
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    float ms_ann = 0, ms_fwd = 0, ms_tb = 0;
+    cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
+    for (const SubBatch &sb : ctx->subs) {
+        AnnotateArgs aa{};
+        aa.chunks = ctx->d_chunks.as<ChunkDesc>(); aa.slots = ctx->d_slots.as<ChunkSlot>() + sb.first;
+        aa.order = ctx->d_order.as<int32_t>() + sb.first; aa.n = sb.count; aa.items = ctx->d_items.as<ItemDesc>();
+        aa.ref_codes = ctx->d_ref.as<uint8_t>(); aa.seq_codes = ctx->d_seq.as<uint8_t>();
+        aa.raw_ref = ctx->d_raw_ref.as<uint8_t>(); aa.raw_seq = ctx->d_raw_seq.as<uint8_t>();
+        aa.nf_ref = ctx->d_nf_ref.as<int32_t>(); aa.lf_ref = ctx->d_lf_ref.as<int32_t>();
+        aa.nf_seq = ctx->d_nf_seq.as<int32_t>(); aa.lf_seq = ctx->d_lf_seq.as<int32_t>();
+        aa.colrec = ctx->d_colrec.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
+        aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l;
+        CU(cudaEventRecord(e0, ctx->stream));
+        annotate_kernel<<<2 * sb.count, ANN_THREADS, 0, ctx->stream>>>(aa);
+        CU(cudaGetLastError()); S.launches++;
+        CU(cudaEventRecord(e1, ctx->stream));
+
+        ForwardArgs fa{};
+        fa.chunks = aa.chunks; fa.slots = aa.slots; fa.order = aa.order; fa.n = sb.count;
+        fa.counter = ctx->d_counter.as<int>(); fa.items = aa.items; fa.bits = ctx->d_bits.as<uint32_t>();
+        fa.ref_codes = aa.ref_codes; fa.seq_codes = aa.seq_codes; fa.colrec = aa.colrec; fa.rowrec = aa.rowrec;
+        fa.tb = ctx->d_tb.as<uint16_t>(); fa.np_tab = ctx->d_np.as<float>(); fa.sub_tab = ctx->d_sub.as<float>();
+        fa.out = ctx->d_chunk_out.as<ChunkOut>();
+        fa.ovf = ctx->d_ovf.as<OverflowRec>(); fa.ovf_count = ctx->d_ovf_count.as<int>(); fa.ovf_cap = npore_ctx::OVF_CAP;
+        fa.P = ctx->P;
+        CU(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
+        int rc = NPORE_OK;
+        switch (ctx->cpl) {
+        case 1: rc = launch_forward<1>(ctx, fa, sb.count); break;
+        case 2: rc = launch_forward<2>(ctx, fa, sb.count); break;
+        case 4: rc = launch_forward<4>(ctx, fa, sb.count); break;
+        default: rc = launch_forward<8>(ctx, fa, sb.count); break;
+        }
+        if (rc != NPORE_OK) return rc;
+        S.launches++;
+        CU(cudaEventRecord(e2, ctx->stream));
+
+        TracebackArgs ta{};
+        ta.chunks = aa.chunks; ta.slots = aa.slots; ta.order = aa.order; ta.n = sb.count; ta.items = aa.items;
+        ta.bits = fa.bits; ta.cum = ctx->d_cum.as<uint32_t>(); ta.ref_codes = aa.ref_codes; ta.seq_codes = aa.seq_codes;
+        ta.tb = fa.tb; ta.ops = ctx->d_scratch_ops.as<uint8_t>(); ta.out = fa.out;
+        ta.ovf = fa.ovf; ta.ovf_count = fa.ovf_count; ta.ovf_cap = fa.ovf_cap;
+        ta.r = ctx->P.r; ta.W = ctx->P.W; ta.cpl = ctx->cpl; ta.tbs = ctx->tbs;
+        traceback_kernel<<<(sb.count + TB_THREADS - 1) / TB_THREADS, TB_THREADS, 0, ctx->stream>>>(ta);
+        CU(cudaGetLastError()); S.launches++;
+        CU(cudaEventRecord(e3, ctx->stream));
+        CU(cudaEventSynchronize(e3));
+        float t;
+        cudaEventElapsedTime(&t, e0, e1); ms_ann += t;
+        cudaEventElapsedTime(&t, e1, e2); ms_fwd += t;
+        cudaEventElapsedTime(&t, e2, e3); ms_tb += t;
+        for (int k = 0; k < sb.count; k++) S.tb_bytes += (int64_t)ctx->chunk_bmax[ctx->order[sb.first + k]] * 64 * ctx->tbs;
+    }
+    // ---- finish
+    CU(cudaEventRecord(e0, ctx->stream));
+    if (n) {
+        FinishArgs fa{};
+        fa.items = ctx->d_items.as<ItemDesc>(); fa.n_items = n; fa.chunk_out = ctx->d_chunk_out.as<ChunkOut>();
+        fa.scratch = ctx->d_scratch_ops.as<uint8_t>(); fa.ops = ctx->d_ops.as<uint8_t>();
+        fa.item_len = ctx->d_item_len.as<int32_t>(); fa.item_status = ctx->d_item_status.as<int32_t>();
+        fa.ref_codes = ctx->d_ref.as<uint8_t>(); fa.seq_codes = ctx->d_seq.as<uint8_t>();
+        fa.rle = ctx->d_rle_out.as<uint32_t>(); fa.rle_len = ctx->d_rle_len.as<int32_t>();
+        gather_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
+        CU(cudaGetLastError()); S.launches++;
+        if (flags & NPORE_OUT_STANDARDIZE) {
+            standardize_kernel<<<(n + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(fa);
+            CU(cudaGetLastError()); S.launches++;
+        }
+        if (flags & NPORE_OUT_RLE) {
+            rle_kernel<<<(n + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(fa);
+            CU(cudaGetLastError()); S.launches++;
+        }
+    }
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&S.ms_plan, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&S.ms_finish, e0, e1);
+    cudaEventElapsedTime(&S.ms_kernels_total, ctx->ev[2], e1);
+    S.ms_annotate = ms_ann; S.ms_forward = ms_fwd; S.ms_traceback = ms_tb;
+    S.n_sub_batches = (int)ctx->subs.size();
+    int ovf = 0;
+    CU(cudaMemcpy(&ovf, ctx->d_ovf_count.p, 4, cudaMemcpyDeviceToHost));
+    S.overflow_runs = ovf;
+    if (ovf > npore_ctx::OVF_CAP) return fail(ctx, NPORE_ERR_CAPACITY, "run-overflow list exhausted");
+    ctx->ran = true;
+    return NPORE_OK;
+}
+
+int npore_download(npore_ctx *ctx, npore_result *res)
+{
+    if (!ctx || !res) return NPORE_ERR_BAD_ARG;
+    if (!ctx->ran) return fail(ctx, NPORE_ERR_STATE, "npore_download before npore_run");
+    CU(cudaSetDevice(ctx->device));
+    const int n = (int)ctx->items.size();
+    const uint32_t flags = ctx->run_flags;
+    const bool want_ops = !(flags & NPORE_OUT_NO_EXPANDED) && res->ops && res->ops_off;
+    const bool want_rle = (flags & NPORE_OUT_RLE) && res->rle && res->rle_off;
+    npore_stats &S = ctx->stats;
+    S.d2h_bytes = 0;
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    // small arrays: item_len, item_status, rle_len, chunk_out
+    const size_t small_bytes = (size_t)n * 12 + (size_t)ctx->n_chunks * sizeof(ChunkOut) + 64;
+    CU(ctx->h_small.ensure(small_bytes));
+    int32_t *h_len = (int32_t *)ctx->h_small.p, *h_status = h_len + n, *h_rlen = h_status + n;
+    ChunkOut *h_co = (ChunkOut *)(h_rlen + n + (n & 1));
+    if (n) {
+        CU(cudaMemcpyAsync(h_len, ctx->d_item_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h_status, ctx->d_item_status.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (flags & NPORE_OUT_RLE) CU(cudaMemcpyAsync(h_rlen, ctx->d_rle_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->n_chunks) CU(cudaMemcpyAsync(h_co, ctx->d_chunk_out.p, sizeof(ChunkOut) * (size_t)ctx->n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
+        S.d2h_bytes += (int64_t)n * 12 + (int64_t)ctx->n_chunks * sizeof(ChunkOut);
+    }
+    if (want_ops && ctx->total_ops) {
+        CU(ctx->h_ops.ensure((size_t)ctx->total_ops));
+        CU(cudaMemcpyAsync(ctx->h_ops.p, ctx->d_ops.p, (size_t)ctx->total_ops, cudaMemcpyDeviceToHost, ctx->stream));
+        S.d2h_bytes += ctx->total_ops;
+    }
+    if (want_rle && ctx->total_ops) {
+        CU(ctx->h_rle.ensure((size_t)ctx->total_ops * 4));
+        // only the used prefix of each item's region matters, but regions are interleaved: copy all (TODO: device pack)
+        CU(cudaMemcpyAsync(ctx->h_rle.p, ctx->d_rle_out.p, (size_t)ctx->total_ops * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        S.d2h_bytes += ctx->total_ops * 4;
+    }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&S.ms_d2h, ctx->ev[0], ctx->ev[1]);
+
+    int64_t o = 0, ro = 0, so = 0;
+    for (int i = 0; i < n; i++) {
+        const ItemDesc &I = ctx->items[i];
+        if (res->status) res->status[i] = h_status[i];
+        if (want_ops) {
+            res->ops_off[i] = o;
+            if (o + h_len[i] > res->ops_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "ops buffer too small");
+            memcpy(res->ops + o, (const uint8_t *)ctx->h_ops.p + I.out_off, (size_t)h_len[i]);
+            o += h_len[i];
+        }
+        if (want_rle) {
+            res->rle_off[i] = ro;
+            if (ro + h_rlen[i] > res->rle_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "rle buffer too small");
+            memcpy(res->rle + ro, (const uint32_t *)ctx->h_rle.p + I.out_off, 4 * (size_t)h_rlen[i]);
+            ro += h_rlen[i];
+        }
+        if (res->chunk_scores && res->score_off) {
+            res->score_off[i] = so;
+            if (so + I.n_chunks > res->score_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "score buffer too small");
+            for (int k = 0; k < I.n_chunks; k++) res->chunk_scores[so + k] = h_co[I.chunk_first + k].score;
+            so += I.n_chunks;
+        }
+    }
+    if (want_ops) res->ops_off[n] = o;
+    if (want_rle) res->rle_off[n] = ro;
+    if (res->chunk_scores && res->score_off) res->score_off[n] = so;
+    return NPORE_OK;
+}
+
+int npore_align_batch(npore_ctx *ctx, const npore_batch *batch, uint32_t flags, npore_result *result)
+{
+    int rc = npore_upload(ctx, batch);
+    if (rc != NPORE_OK) return rc;
+    rc = npore_run(ctx, flags);
+    if (rc != NPORE_OK) return rc;
+    return npore_download(ctx, result);
+}
+
+int npore_get_np_info(npore_ctx *ctx, const uint8_t *codes, int32_t len, int32_t *out)
+{
+    if (!ctx || len < 0 || (len && (!codes || !out))) return NPORE_ERR_BAD_ARG;
+    if (len == 0) return NPORE_OK;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d_s, d_raw, d_nf, d_lf, d_out;
+    const size_t ob = (size_t)len * 2 * ctx->P.max_n * sizeof(int32_t);
+    int rc = NPORE_OK;
+    if (d_s.ensure(len) != cudaSuccess || d_raw.ensure((size_t)len * 8) != cudaSuccess || d_nf.ensure((size_t)len * 4) != cudaSuccess ||
+        d_lf.ensure((size_t)len * 4) != cudaSuccess || d_out.ensure(std::max<size_t>(ob, 4)) != cudaSuccess) rc = fail(ctx, NPORE_ERR_OOM, "np_info scratch");
+    if (rc == NPORE_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_s.p, codes, len, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) {
+            np_info_kernel<<<1, ANN_THREADS, 0, ctx->stream>>>(d_s.as<uint8_t>(), len, ctx->P.max_n, ctx->P.max_l, d_raw.as<uint8_t>(),
+                                                               d_nf.as<int32_t>(), d_lf.as<int32_t>(), d_out.as<int32_t>());
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess && ob) e = cudaMemcpyAsync(out, d_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, NPORE_ERR_CUDA, "np_info", e);
+    }
+    d_s.release(); d_raw.release(); d_nf.release(); d_lf.release(); d_out.release();
+    return rc;
+}
+
+int npore_last_stats(const npore_ctx *ctx, npore_stats *stats)
+{
+    if (!ctx || !stats) return NPORE_ERR_BAD_ARG;
+    *stats = ctx->stats;
+    return NPORE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""Host side of the GPU batch scheduler: packs items into the flat buffers of the C ABI and drives
+libnpore_b200.so.  Replaces the reference's Pool fan-out (/root/reference/src/realign.py:110-114,
+standardize_vcf.py:30-31): one `Realigner.run()` call = one batch on one B200.
+
+PyTorch is used only to allocate pinned host buffers (and to pick the CUDA device); all compute is in the
+CUDA library.  There is no CPU path: constructing a Realigner without a GPU raises.
+"""
+import ctypes as C
+import re
+
+import numpy as np
+
+from . import _lib
+from ._lib import NPORE_OUT_NO_EXPANDED, NPORE_OUT_RLE, NPORE_OUT_STANDARDIZE  # noqa: F401
+
+_RLE = re.compile(rb"(\d+)([MIDNSHP=XB])")
+_OPCODE = np.full(256, 255, dtype=np.uint8)
+for _k, _c in enumerate("MIDNSHP=XB"):            # cfg.py:27-32
+    _OPCODE[ord(_c)] = _k
+_OPCHAR = np.frombuffer(b"MIDNSHP=XB", dtype=np.uint8)
+
+
+class NporeError(RuntimeError):
+    pass
+
+
+def _pinned(n, dtype):
+    """Pinned host array (numpy view of a torch pinned tensor); falls back to pageable if torch has no CUDA."""
+    import torch
+    n = max(int(n), 1)
+    if torch.cuda.is_available():
+        t = torch.empty(n, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        return t.numpy(), t          # the numpy view keeps the pinned storage alive
+    return np.empty(n, dtype=dtype), None
+
+
+def cigar_to_rle(cigar: str) -> np.ndarray:
+    """CIGAR text -> BAM-style words (len<<4|op).  Accepts run-length text ('3=2D') or expanded text ('===DD').
+    S and H groups are dropped (bam.pyx:59)."""
+    b = cigar.encode("latin-1")
+    if not b:
+        return np.zeros(0, np.uint32)
+    if b[0] in b"0123456789":
+        m = _RLE.findall(b)
+        lens = np.array([int(x) for x, _ in m], dtype=np.uint32)
+        ops = _OPCODE[np.frombuffer(b"".join(o for _, o in m), dtype=np.uint8)].astype(np.uint32)
+    else:
+        a = np.frombuffer(b, dtype=np.uint8)
+        cut = np.flatnonzero(a[1:] != a[:-1]) + 1
+        starts = np.concatenate(([0], cut))
+        lens = np.diff(np.concatenate((starts, [len(a)]))).astype(np.uint32)
+        ops = _OPCODE[a[starts]].astype(np.uint32)
+    keep = (ops != 4) & (ops != 5)
+    return ((lens[keep] << 4) | ops[keep]).astype(np.uint32)
+
+
+def rle_to_text(words: np.ndarray) -> str:
+    """words (len<<4|op) -> '12M1I...' (cig.pyx:13-38 collapse_cigar output)."""
+    if len(words) == 0:
+        return ""
+    lens = (words >> 4).tolist()
+    ops = _OPCHAR[words & 15].tobytes().decode()
+    return "".join(f"{n}{o}" for n, o in zip(lens, ops))
+
+
+class PackedBatch:
+    """Flat host buffers in the layout of `npore_batch` (include/npore_b200.h)."""
+
+    def __init__(self, refs, seqs, cigars, shared_ref=None, ref_ranges=None, pinned=True):
+        """refs/seqs: lists of uint8 code arrays; cigars: list of RLE word arrays.
+        shared_ref + ref_ranges[(start, stop)]: items index one shared reference (region sharding)."""
+        n = len(seqs)
+        self.n = n
+        alloc = (lambda m, dt: _pinned(m, dt)[0]) if pinned else (lambda m, dt: np.empty(max(int(m), 1), dtype=dt))
+        self.seq_len = np.array([len(s) for s in seqs], dtype=np.int32)
+        self.seq_start = np.zeros(n, dtype=np.int64)
+        if n:
+            np.cumsum(self.seq_len[:-1], out=self.seq_start[1:])
+        self.seq_total = int(self.seq_len.sum())
+        self.seq_codes = alloc(self.seq_total, np.uint8)
+        if self.seq_total:
+            np.concatenate(seqs, out=self.seq_codes[:self.seq_total])
+        if shared_ref is not None:
+            self.ref_total = int(len(shared_ref))
+            self.ref_codes = alloc(self.ref_total, np.uint8)
+            self.ref_codes[:self.ref_total] = shared_ref
+            self.ref_start = np.array([a for a, _ in ref_ranges], dtype=np.int64)
+            self.ref_len = np.array([b - a for a, b in ref_ranges], dtype=np.int32)
+        else:
+            self.ref_len = np.array([len(s) for s in refs], dtype=np.int32)
+            self.ref_start = np.zeros(n, dtype=np.int64)
+            if n:
+                np.cumsum(self.ref_len[:-1], out=self.ref_start[1:])
+            self.ref_total = int(self.ref_len.sum())
+            self.ref_codes = alloc(self.ref_total, np.uint8)
+            if self.ref_total:
+                np.concatenate(refs, out=self.ref_codes[:self.ref_total])
+        self.cigar_off = np.zeros(n + 1, dtype=np.int64)
+        if n:
+            np.cumsum([len(c) for c in cigars], out=self.cigar_off[1:])
+        self.cigar_rle = alloc(int(self.cigar_off[-1]), np.uint32)
+        if int(self.cigar_off[-1]):
+            np.concatenate(cigars, out=self.cigar_rle[:int(self.cigar_off[-1])])
+        self.total_ops = int(self.ref_len.astype(np.int64).sum() + self.seq_len.astype(np.int64).sum())
+
+    def c_struct(self):
+        p = lambda a: a.ctypes.data  # noqa: E731
+        return _lib.Batch(self.n, p(self.ref_codes), p(self.ref_start), p(self.ref_len), self.ref_total,
+                          p(self.seq_codes), p(self.seq_start), p(self.seq_len), self.seq_total,
+                          p(self.cigar_rle), p(self.cigar_off))
+
+    def h2d_bytes(self):
+        return self.ref_total + self.seq_total + 4 * int(self.cigar_off[-1])
+
+
+class BatchResult:
+    def __init__(self, n, total_ops, n_chunks, want_rle, pinned=True):
+        alloc = (lambda m, dt: _pinned(m, dt)[0]) if pinned else (lambda m, dt: np.empty(max(int(m), 1), dtype=dt))
+        self.n = n
+        self.ops = alloc(total_ops, np.uint8)
+        self.ops_off = np.zeros(n + 1, dtype=np.int64)
+        self.rle = alloc(total_ops if want_rle else 1, np.uint32)
+        self.rle_off = np.zeros(n + 1, dtype=np.int64)
+        self.chunk_scores = np.zeros(max(n_chunks, 1), dtype=np.float32)
+        self.score_off = np.zeros(n + 1, dtype=np.int64)
+        self.status = np.zeros(max(n, 1), dtype=np.int32)
+        self.want_rle = want_rle
+
+    def c_struct(self):
+        p = lambda a: a.ctypes.data  # noqa: E731
+        return _lib.Result(p(self.ops), len(self.ops), p(self.ops_off),
+                           p(self.rle) if self.want_rle else None, len(self.rle), p(self.rle_off) if self.want_rle else None,
+                           p(self.chunk_scores), len(self.chunk_scores), p(self.score_off), p(self.status))
+
+    def ops_str(self, i) -> str:
+        return self.ops[self.ops_off[i]:self.ops_off[i + 1]].tobytes().decode()
+
+    def rle_words(self, i) -> np.ndarray:
+        return self.rle[self.rle_off[i]:self.rle_off[i + 1]]
+
+    def cigar_text(self, i) -> str:
+        return rle_to_text(self.rle_words(i))
+
+    def scores(self, i) -> np.ndarray:
+        return self.chunk_scores[self.score_off[i]:self.score_off[i + 1]]
+
+
+class Realigner:
+    """One GPU context (npore_ctx).  Parameters mirror align()'s (aln.pyx:379-382) and cfg.args.max_n/max_l."""
+
+    def __init__(self, sub_scores, np_scores, max_n=6, max_l=100, indel_start=5.0, indel_extend=1.0,
+                 max_b_rows=20000, r=30, device=0):
+        self._ctx = C.c_void_p()
+        self._L = _lib.lib()
+        sub = np.ascontiguousarray(sub_scores, dtype=np.float32)
+        npt = np.ascontiguousarray(np_scores, dtype=np.float32)
+        if sub.shape != (5, 5) or npt.ndim != 3 or npt.shape[1] != npt.shape[2]:
+            raise ValueError("sub_scores must be [5,5], np_scores [n, l, l]")
+        self.params = dict(max_n=max_n, max_l=max_l, indel_start=indel_start, indel_extend=indel_extend,
+                           max_b_rows=max_b_rows, r=r, device=device)
+        rc = self._L.npore_ctx_create(C.byref(self._ctx), device, sub.ctypes.data, npt.ctypes.data, npt.shape[0], npt.shape[1],
+                                      max_n, max_l, indel_start, indel_extend, max_b_rows, r)
+        if rc != 0:
+            self._ctx = C.c_void_p()
+            raise NporeError(f"npore_ctx_create failed: {self._L.npore_strerror(rc).decode()} "
+                             "(npore_b200 needs a CUDA device; there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._L.npore_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NporeError(f"{what}: {self._L.npore_strerror(rc).decode()} [{self._L.npore_last_error(self._ctx).decode()}]")
+
+    def count_chunks(self, packed: PackedBatch) -> int:
+        return int(self._L.npore_count_chunks(self._ctx, packed.n, packed.ref_len.ctypes.data, packed.seq_len.ctypes.data))
+
+    def new_result(self, packed: PackedBatch, flags: int, pinned=True) -> BatchResult:
+        return BatchResult(packed.n, packed.total_ops, self.count_chunks(packed), bool(flags & NPORE_OUT_RLE), pinned)
+
+    # three-phase API (npore_upload / npore_run / npore_download)
+    def upload(self, packed: PackedBatch):
+        b = packed.c_struct()
+        self._check(self._L.npore_upload(self._ctx, C.byref(b)), "npore_upload")
+
+    def run(self, flags: int = 0):
+        self._check(self._L.npore_run(self._ctx, flags), "npore_run")
+
+    def download(self, result: BatchResult):
+        r = result.c_struct()
+        self._check(self._L.npore_download(self._ctx, C.byref(r)), "npore_download")
+        return result
+
+    def align_packed(self, packed: PackedBatch, flags: int = 0, result: BatchResult = None) -> BatchResult:
+        """npore_align_batch: host buffers in, host buffers out."""
+        result = result or self.new_result(packed, flags)
+        b, r = packed.c_struct(), result.c_struct()
+        self._check(self._L.npore_align_batch(self._ctx, C.byref(b), flags, C.byref(r)), "npore_align_batch")
+        return result
+
+    def stats(self) -> dict:
+        s = _lib.Stats()
+        self._check(self._L.npore_last_stats(self._ctx, C.byref(s)), "npore_last_stats")
+        return s.as_dict()
+
+    def get_np_info(self, codes: np.ndarray) -> np.ndarray:
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        out = np.zeros((max(len(codes), 1), 2, self.params["max_n"]), dtype=np.int32)
+        self._check(self._L.npore_get_np_info(self._ctx, codes.ctypes.data if len(codes) else None, len(codes), out.ctypes.data), "npore_get_np_info")
+        return out[:len(codes)]
+
+    # convenience: python objects in, python objects out
+    def align_many(self, refs, seqs, cigars, standardize=False, collapse=False):
+        """refs/seqs: lists of uint8 code arrays; cigars: CIGAR texts (run-length or expanded).
+        Returns (list of CIGAR strings, list of per-chunk score arrays, status array)."""
+        rles = [cigar_to_rle(c) for c in cigars]
+        packed = PackedBatch([np.ascontiguousarray(r, dtype=np.uint8) for r in refs],
+                             [np.ascontiguousarray(s, dtype=np.uint8) for s in seqs], rles, pinned=False)
+        flags = (NPORE_OUT_STANDARDIZE if standardize else 0) | (NPORE_OUT_RLE if collapse else 0)
+        res = self.align_packed(packed, flags, self.new_result(packed, flags, pinned=False))
+        if collapse:
+            outs = [res.cigar_text(i) for i in range(packed.n)]
+        else:
+            outs = [res.ops_str(i) for i in range(packed.n)]
+        return outs, [res.scores(i).copy() for i in range(packed.n)], res.status[:packed.n].copy()
