@@ -116,6 +116,10 @@ int  npore_ctx_create(npore_ctx **out, int device,
                       float indel_start, float indel_extend, int max_b_rows, int r);
 void npore_ctx_destroy(npore_ctx *ctx);
 
+/* run all copies and kernels of this context on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
+ * stream) instead of the context's own; the caller keeps ownership of the stream */
+int  npore_set_stream(npore_ctx *ctx, void *cuda_stream);
+
 /* number of chunks align() will cut the batch into (src/aln.pyx:344-358): capacity for chunk_scores */
 int64_t npore_count_chunks(const npore_ctx *ctx, int32_t n_items, const int32_t *ref_len, const int32_t *seq_len);
 

@@ -38,7 +38,7 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_count_chunks", "npore_upload", "npore_run", "npore_download",
+EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_set_stream", "npore_count_chunks", "npore_upload", "npore_run", "npore_download",
            "npore_align_batch", "npore_get_np_info", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
 
 _lib = None
@@ -55,6 +55,7 @@ def lib():
                                        C.c_float, C.c_float, C.c_int, C.c_int]
         L.npore_ctx_destroy.argtypes = [C.c_void_p]
         L.npore_ctx_destroy.restype = None
+        L.npore_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.npore_count_chunks.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.npore_count_chunks.restype = C.c_int64
         L.npore_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]

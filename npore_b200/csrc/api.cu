@@ -64,6 +64,7 @@ struct SubBatch { int first, count; };
 struct npore_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
     AlignParams P{};
     int cpl = 2, tbs = 2, np_n = 0;
     size_t scratch_budget = 0;
@@ -84,6 +85,7 @@ struct npore_ctx {
     uint32_t run_flags = 0;
     npore_stats stats{};
     cudaEvent_t ev[8]{};
+    std::vector<cudaEvent_t> sub_ev;     // 4 per sub-batch
     std::string err;
     static const int OVF_CAP = 1 << 16;
 };
@@ -206,8 +208,20 @@ void npore_ctx_destroy(npore_ctx *ctx)
     for (auto *b : bufs) b->release();
     ctx->h_ops.release(); ctx->h_rle.release(); ctx->h_small.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (auto &e : ctx->sub_ev) cudaEventDestroy(e);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+int npore_set_stream(npore_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return NPORE_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return NPORE_OK;
 }
 
 int64_t npore_count_chunks(const npore_ctx *ctx, int32_t n_items, const int32_t *ref_len, const int32_t *seq_len)
@@ -364,8 +378,12 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     }
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     float ms_ann = 0, ms_fwd = 0, ms_tb = 0;
-    cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5], e2 = ctx->ev[6], e3 = ctx->ev[7];
-    for (const SubBatch &sb : ctx->subs) {
+    while (ctx->sub_ev.size() < 4 * ctx->subs.size()) {
+        cudaEvent_t e; CU(cudaEventCreate(&e)); ctx->sub_ev.push_back(e);
+    }
+    for (size_t si = 0; si < ctx->subs.size(); si++) {
+        const SubBatch &sb = ctx->subs[si];
+        cudaEvent_t e0 = ctx->sub_ev[4 * si], e1 = ctx->sub_ev[4 * si + 1], e2 = ctx->sub_ev[4 * si + 2], e3 = ctx->sub_ev[4 * si + 3];
         AnnotateArgs aa{};
         aa.chunks = ctx->d_chunks.as<ChunkDesc>(); aa.slots = ctx->d_slots.as<ChunkSlot>() + sb.first;
         aa.order = ctx->d_order.as<int32_t>() + sb.first; aa.n = sb.count; aa.items = ctx->d_items.as<ItemDesc>();
@@ -409,14 +427,10 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         traceback_kernel<<<(sb.count + TB_THREADS - 1) / TB_THREADS, TB_THREADS, 0, ctx->stream>>>(ta);
         CU(cudaGetLastError()); S.launches++;
         CU(cudaEventRecord(e3, ctx->stream));
-        CU(cudaEventSynchronize(e3));
-        float t;
-        cudaEventElapsedTime(&t, e0, e1); ms_ann += t;
-        cudaEventElapsedTime(&t, e1, e2); ms_fwd += t;
-        cudaEventElapsedTime(&t, e2, e3); ms_tb += t;
         for (int k = 0; k < sb.count; k++) S.tb_bytes += (int64_t)ctx->chunk_bmax[ctx->order[sb.first + k]] * 64 * ctx->tbs;
     }
     // ---- finish
+    cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5];
     CU(cudaEventRecord(e0, ctx->stream));
     if (n) {
         FinishArgs fa{};
@@ -438,6 +452,12 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     }
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    for (size_t si = 0; si < ctx->subs.size(); si++) {
+        float t;
+        cudaEventElapsedTime(&t, ctx->sub_ev[4 * si], ctx->sub_ev[4 * si + 1]); ms_ann += t;
+        cudaEventElapsedTime(&t, ctx->sub_ev[4 * si + 1], ctx->sub_ev[4 * si + 2]); ms_fwd += t;
+        cudaEventElapsedTime(&t, ctx->sub_ev[4 * si + 2], ctx->sub_ev[4 * si + 3]); ms_tb += t;
+    }
     cudaEventElapsedTime(&S.ms_plan, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&S.ms_finish, e0, e1);
     cudaEventElapsedTime(&S.ms_kernels_total, ctx->ev[2], e1);

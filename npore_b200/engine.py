@@ -176,6 +176,10 @@ class Realigner:
         if rc != 0:
             raise NporeError(f"{what}: {self._L.npore_strerror(rc).decode()} [{self._L.npore_last_error(self._ctx).decode()}]")
 
+    def set_stream(self, cuda_stream: int):
+        """Run on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._check(self._L.npore_set_stream(self._ctx, C.c_void_p(cuda_stream)), "npore_set_stream")
+
     def count_chunks(self, packed: PackedBatch) -> int:
         return int(self._L.npore_count_chunks(self._ctx, packed.n, packed.ref_len.ctypes.data, packed.seq_len.ctypes.data))
 

@@ -56,59 +56,124 @@ def call_length_model(np_scores: np.ndarray):
     return p
 
 
-def make_read(ref: str, rng: np.random.Generator, call_model=None, p_ins=0.01, p_sub=0.015, p_del=0.015,
-              alphabet: str = BASES):
-    """Returns (seq, expanded_cigar over =XID) for a read covering the whole of `ref`."""
-    tr = {s: (n, c) for s, n, c in _tracts(ref)}
-    seq, cig, i, L = [], [], 0, len(ref)
-    while i < L:
-        t = tr.get(i)
-        if t is not None and call_model is not None:
-            n, c = t
-            cc = min(c, call_model.shape[1] - 1)
-            called = int(rng.choice(call_model.shape[2], p=call_model[n - 1, cc]))
-            called = max(0, called + (c - cc))
-            unit = ref[i:i + n]
-            keep = min(c, called)
-            seq.append(unit * keep)
-            cig.append("=" * (keep * n))
-            if called > c:
-                seq.append(unit * (called - c))
-                cig.append("I" * ((called - c) * n))
-            elif called < c:
-                cig.append("D" * ((c - called) * n))
-            i += n * c
-            continue
-        u = rng.random()
-        if u < p_ins:
-            seq.append(alphabet[int(rng.integers(len(alphabet)))])
-            cig.append("I")
-        elif u < p_ins + p_del:
-            cig.append("D")
-            i += 1
-        elif u < p_ins + p_del + p_sub:
-            alt = [b for b in alphabet if b != ref[i]] or [ref[i]]
-            seq.append(alt[int(rng.integers(len(alt)))])
-            cig.append("X" if seq[-1] != ref[i] else "=")
-            i += 1
+def make_reference_with_tracts(length: int, rng: np.random.Generator, p_np: float = 0.3, alphabet: str = BASES):
+    """Like make_reference, also returning the emitted tracts as an int array [T,3] = (start, n, copies)."""
+    parts, tr, total = [], [], 0
+    letters = np.array(list(alphabet))
+    while total < length:
+        if rng.random() < p_np:
+            n = int(rng.integers(1, 7))
+            unit = "".join(letters[rng.integers(0, len(letters), size=n)])
+            copies = min(60, 3 + int(rng.geometric(0.25)))
+            s = unit * copies
+            if total + len(s) <= length:
+                tr.append((total, n, copies))
         else:
-            seq.append(ref[i])
-            cig.append("=")
-            i += 1
-    return "".join(seq), "".join(cig)
+            s = "".join(letters[rng.integers(0, len(letters), size=int(rng.integers(5, 41)))])
+        parts.append(s)
+        total += len(s)
+    return "".join(parts)[:length], np.array(tr, dtype=np.int64).reshape(-1, 3)
 
 
-def make_reads(reference: str, n_reads: int, read_len: int, rng: np.random.Generator, call_model=None):
+def call_length_cdf(call_model):
+    return np.cumsum(call_model, axis=2)
+
+
+def make_read(ref: str, rng: np.random.Generator, call_model=None, p_ins=0.01, p_sub=0.015, p_del=0.015,
+              alphabet: str = BASES, tracts=None):
+    """ONT-like read over the whole of `ref` (Appendix D.2), vectorised.  Returns (seq, expanded CIGAR in =XID).
+    tracts: int array [T,3] of (start, n, copies) inside ref (non-overlapping); scanned from ref if None.
+    Tract copy-number errors are drawn from call_model[n-1, copies] and placed at the tract end; every other
+    base gets independent ins-before / sub / del noise."""
+    L = len(ref)
+    if L == 0:
+        return "", ""
+    if tracts is None:
+        tracts = np.array(_tracts(ref), dtype=np.int64).reshape(-1, 3)
+    rb = np.frombuffer(ref.encode(), dtype=np.uint8)
+    letters = np.frombuffer(alphabet.encode(), dtype=np.uint8)
+    op = np.full(L, ord("="), dtype=np.uint8)
+    base = rb.copy()
+    n_ins = np.zeros(L, dtype=np.int64)          # bases inserted AFTER ref position p
+    ins_src = np.full(L, -1, dtype=np.int64)     # >=0: inserted bases copy ref[ins_src + k % ins_n]; -1: random
+    ins_n = np.ones(L, dtype=np.int64)
+    noisy = np.ones(L, dtype=bool)
+    if call_model is not None and len(tracts):
+        st, n, c = tracts[:, 0], tracts[:, 1], tracts[:, 2]
+        cc = np.minimum(c, call_model.shape[1] - 1)
+        cdf = np.cumsum(call_model[n - 1, cc], axis=1)
+        called = (cdf < rng.random(len(st))[:, None]).sum(axis=1)
+        called = np.maximum(0, np.minimum(called, call_model.shape[2] - 1) + (c - cc))
+        for s0, n0, c0, k0 in zip(st.tolist(), n.tolist(), c.tolist(), called.tolist()):
+            e0 = s0 + n0 * c0
+            noisy[s0:e0] = False
+            if k0 < c0:
+                op[e0 - (c0 - k0) * n0:e0] = ord("D")
+            elif k0 > c0:
+                n_ins[e0 - 1] = (k0 - c0) * n0
+                ins_src[e0 - 1] = s0
+                ins_n[e0 - 1] = n0
+    m = int(noisy.sum())
+    if m and (p_ins or p_sub or p_del):
+        u = rng.random(m)
+        idx = np.flatnonzero(noisy)
+        dele = u < p_del
+        sub = (u >= p_del) & (u < p_del + p_sub)
+        op[idx[dele]] = ord("D")
+        si = idx[sub]
+        if len(si) and len(letters) > 1:
+            cur = np.searchsorted(np.sort(letters), base[si])
+            srt = np.sort(letters)
+            base[si] = srt[(cur + rng.integers(1, len(letters), size=len(si))) % len(letters)]
+            op[si] = np.where(base[si] != rb[si], ord("X"), ord("="))
+        ins = idx[rng.random(m) < p_ins]
+        ins = ins[n_ins[ins] == 0]
+        n_ins[ins] = 1
+    # assemble: for every ref position its op (and base unless D), then its inserted bases
+    counts = np.empty(2 * L, dtype=np.int64)
+    counts[0::2] = 1
+    counts[1::2] = n_ins
+    cig2 = np.empty(2 * L, dtype=np.uint8)
+    cig2[0::2] = op
+    cig2[1::2] = ord("I")
+    cig = np.repeat(cig2, counts)
+    total = int(counts.sum())
+    owner = np.repeat(np.arange(2 * L), counts)              # which slot produced each output op
+    pos = owner >> 1
+    is_ins = (owner & 1).astype(bool)
+    first = np.cumsum(counts) - counts                        # start offset of each slot
+    k = np.arange(total) - first[owner]
+    seqb = base[pos].copy()
+    src = ins_src[pos]
+    tract_ins = is_ins & (src >= 0)
+    seqb[tract_ins] = rb[src[tract_ins] + k[tract_ins] % ins_n[pos[tract_ins]]]
+    rnd = is_ins & (src < 0)
+    seqb[rnd] = letters[rng.integers(0, len(letters), size=int(rnd.sum()))]
+    keep = cig != ord("D")
+    return seqb[keep].tobytes().decode(), cig.tobytes().decode()
+
+
+def make_reads(reference: str, n_reads: int, read_len: int, rng: np.random.Generator, call_model=None, tracts=None):
     """List of read_data tuples shaped like bam.pyx:34-47:
-    (read_id, flag, ref_name, start, mapq, cigarstring, stop, seq, quals, ref, hap)."""
+    (read_id, flag, ref_name, start, mapq, cigarstring, stop, seq, quals, ref, hap).  Sorted by start."""
     from .cig import collapse_cigar
     out, L = [], len(reference)
     starts = np.sort(rng.integers(0, max(1, L - read_len + 1), size=n_reads))
-    for k, st in enumerate(starts):
-        st = int(st)
-        rs = reference[st:st + read_len]
-        seq, cig = make_read(rs, rng, call_model)
-        out.append((f"read{k}", 0, "ref", st, 60, collapse_cigar(cig), st + len(rs), seq, "*", rs, int(rng.integers(0, 3))))
+    if tracts is None:
+        tracts = np.array(_tracts(reference), dtype=np.int64).reshape(-1, 3)
+    tends = tracts[:, 0] + tracts[:, 1] * tracts[:, 2] if len(tracts) else np.zeros(0, np.int64)
+    for k, st in enumerate(starts.tolist()):
+        en = min(L, st + read_len)
+        rs = reference[st:en]
+        if len(tracts):
+            a = int(np.searchsorted(tracts[:, 0], st, side="left"))
+            b = int(np.searchsorted(tends, en, side="right"))
+            tr = tracts[a:b].copy()
+            tr[:, 0] -= st
+        else:
+            tr = tracts
+        seq, cig = make_read(rs, rng, call_model, tracts=tr)
+        out.append((f"read{k}", 0, "ref", st, 60, collapse_cigar(cig), en, seq, "*", rs, int(rng.integers(0, 3))))
     return out
 
 
