@@ -1,0 +1,240 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (libnpore_b200.so via npore_b200.engine),
+against (a) the golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+Bit-exact for CIGARs / op strings / np_info; DP scores compared bit-for-bit too (stricter than the 1e-5 relative
+tolerance north_star allows: the recurrence is fp32 add + compare in the reference's order)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from npore_b200 import cig, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine_factory(tables):
+    from npore_b200.engine import Realigner
+    made = []
+
+    def make(**kw):
+        e = Realigner(tables[0], tables[1], **kw)
+        made.append(e)
+        return e
+    yield make
+    for e in made:
+        e.close()
+
+
+def _oracle_all(cases, S, NP, **kw):
+    out = []
+    for rf, sq, cg in cases:
+        ir, iq = oracle.bases_to_int(rf), oracle.bases_to_int(sq)
+        o, sc, st = oracle.align(ir, iq, cg, S, NP, return_scores=True, **kw)
+        out.append((o, sc, st, oracle.collapse_cigar(oracle.standardize(o, ir, iq))))
+    return out
+
+
+def _check(eng, cases, want):
+    refs = [oracle.bases_to_int(c[0]) for c in cases]
+    seqs = [oracle.bases_to_int(c[1]) for c in cases]
+    cigs = [c[2] for c in cases]
+    outs, scores, status = eng.align_many(refs, seqs, cigs)
+    std, _, _ = eng.align_many(refs, seqs, cigs, standardize=True, collapse=True)
+    for k, (o, sc, st, sd) in enumerate(want):
+        assert outs[k] == o, f"case {k}: op string differs"
+        assert status[k] == st
+        assert np.array_equal(scores[k], np.asarray(sc, dtype=np.float32)), f"case {k}: chunk scores differ"
+        assert std[k] == sd, f"case {k}: standardised CIGAR differs"
+
+
+def test_fuzz_golden_reference_outputs(tables, golden, engine_factory):
+    """400 seeded cases; expected values come from the compiled reference itself (tests/golden/fuzz.json.gz)."""
+    groups = {}
+    for c in golden("fuzz.json.gz"):
+        groups.setdefault((c["r"], c["max_b_rows"]), []).append(c)
+    for (r, mb), cases in sorted(groups.items()):
+        eng = engine_factory(max_b_rows=mb, r=r)
+        want = [(c["out"], c["scores"], 0, c["std"]) for c in cases]
+        _check(eng, [(c["ref"], c["seq"], c["cigar"]) for c in cases], want)
+
+
+def test_golden_sam_through_realign_reads(tables, golden, tmp_path):
+    """bam.realign_reads on test/data/reads.sam + ref.fasta reproduces test/data/npore_realigned.sam, every field."""
+    from npore_b200 import bam, cfg
+    g = golden("golden_sam.json")
+    cfg.args.sub_scores, cfg.args.np_scores = tables
+    cfg.args.max_n, cfg.args.max_l = 6, 100
+    cfg.args.out_prefix = str(tmp_path / "realigned")
+    lines = bam.realign_reads([tuple(r) for r in g["reads"]])
+    assert lines == g["expected_sam"]
+    assert open(cfg.args.out_prefix + ".sam").read().splitlines() == g["expected_sam"]
+    bam.realign_read(tuple(g["reads"][3]))                                   # per-item entry appends one more line
+    assert open(cfg.args.out_prefix + ".sam").read().splitlines()[-1] == g["expected_sam"][3]
+
+
+def test_align_drop_in_signature(tables, golden):
+    """aln.align with the reference's positional/keyword signature (test/align.py:59-60)."""
+    from npore_b200 import aln, cfg
+    S, NP = tables
+    cfg.args.max_n, cfg.args.max_l = 6, 100
+    for k in golden("align_kats.json"):
+        ir, iq = cig.bases_to_int(k["ref"]), cig.bases_to_int(k["seq"])
+        ex = cig.expand_cigar(k["cigar"])
+        assert aln.align(ir, iq, ex, S, NP, verbose=True, max_b_rows=20, r=10) == k["small"]["out"]
+        assert aln.align(ir, iq, ex, S, NP) == k["default"]["out"]
+    outs, scores = aln.align_batch([cig.bases_to_int(k["ref"]) for k in golden("align_kats.json")],
+                                   [cig.bases_to_int(k["seq"]) for k in golden("align_kats.json")],
+                                   [k["cigar"] for k in golden("align_kats.json")], S, NP, return_scores=True)
+    for k, o, sc in zip(golden("align_kats.json"), outs, scores):
+        assert o == k["default"]["out"]
+        assert np.array_equal(sc, np.array(k["default"]["scores"], dtype=np.float32))
+
+
+def test_np_info_on_device(tables, golden, engine_factory):
+    """aln.pyx:179-251 incl. the docstring example, the >max_l clamp quirk (105 x A) and N bases."""
+    eng = engine_factory()
+    for k in golden("np_info_kats.json"):
+        info = eng.get_np_info(oracle.bases_to_int(k["seq"]))
+        assert info[:, 0, :].T.tolist() == k["L"]
+        assert info[:, 1, :].T.tolist() == k["L_IDX"]
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        s = synth.make_reference(int(rng.integers(1, 3000)), rng, float(rng.choice([0.2, 0.6, 0.95])), str(rng.choice(["ACGT", "AC", "ACGTN"])))
+        if rng.random() < 0.3:
+            k = int(rng.integers(0, len(s)))
+            s = s[:k] + "G" * int(rng.integers(101, 140)) + s[k:]
+        a = oracle.bases_to_int(s)
+        assert np.array_equal(eng.get_np_info(a), oracle.get_np_info(a))
+
+
+def test_realign_haps(tables, golden):
+    """bam.pyx:93-123 on the haplotypes of test/test_std_vcf.vcf."""
+    from npore_b200 import bam, cfg
+    cfg.args.sub_scores, cfg.args.np_scores = tables
+    ks = golden("std_vcf_kats.json")
+    res = bam.realign_haps([(k["contig"], k["hap"], k["seq"], k["ref"], cig.expand_cigar(k["cigar"])) for k in ks])
+    for k, r in zip(ks, res):
+        assert r == (k["contig"], k["hap"], k["seq"], k["ref"], k["out"])
+    assert bam.realign_hap((ks[1]["contig"], ks[1]["hap"], ks[1]["seq"], ks[1]["ref"], cig.expand_cigar(ks[1]["cigar"])))[4] == ks[1]["out"]
+
+
+@pytest.mark.parametrize("r,mb", [(3, 12), (10, 37), (16, 50), (30, 200), (31, 64), (60, 300), (100, 500), (127, 20000)])
+def test_live_fuzz_vs_oracle_all_band_widths(tables, engine_factory, r, mb):
+    """Fresh seeded cases per band width (covers every cells-per-lane template: W<=32, <=64, <=128, <=256)."""
+    S, NP = tables
+    cm = synth.call_length_model(NP)
+    rng = np.random.default_rng(1000 + r)
+    cases = []
+    for _ in range(60):
+        rf, sq, cg, _, _ = synth.fuzz_case(rng, cm)
+        cases.append((rf, sq, cg))
+    cases += [("", "", ""), ("A", "", "D"), ("", "C", "I"), ("ACGT", "ACGT", "MMMM")]     # empty / one-sided items
+    _check(engine_factory(max_b_rows=mb, r=r), cases, _oracle_all(cases, S, NP, max_b_rows=mb, r=r))
+
+
+@pytest.mark.parametrize("max_n", [0, 1, 3])
+def test_reduced_max_n(tables, engine_factory, max_n):
+    """cfg.args.max_n < 6 (max_n = 0 is the affine-only mode of SURVEY.md 8(c))."""
+    S, NP = tables
+    cm = synth.call_length_model(NP)
+    rng = np.random.default_rng(77 + max_n)
+    cases = [synth.fuzz_case(rng, cm)[:3] for _ in range(40)]
+    _check(engine_factory(max_b_rows=150, r=10, max_n=max_n), cases, _oracle_all(cases, S, NP, max_b_rows=150, r=10, max_n=max_n))
+
+
+def test_production_scale_reads_vs_oracle(tables, engine_factory):
+    """48 ONT-like 10 kb reads at align()'s defaults (r=30, max_b_rows=20000), incl. reads that need a second chunk."""
+    S, NP = tables
+    rng = np.random.default_rng(20260101)
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(200_000, rng)
+    reads = synth.make_reads(ref, 40, 10_000, rng, cm, tracts=tr) + synth.make_reads(ref, 8, 10_300, rng, cm, tracts=tr)
+    cases = [(r[9], r[7], cig.expand_cigar(r[5])) for r in reads]
+    want = _oracle_all(cases, S, NP)
+    assert max(len(w[1]) for w in want) == 2                                   # some reads are cut into two chunks
+    _check(engine_factory(), cases, want)
+
+
+def test_long_indel_runs_overflow_path(tables, engine_factory):
+    """INDEL runs longer than the 13-bit run field of the traceback record go through the overflow list."""
+    S, NP = tables
+    rng = np.random.default_rng(4)
+    core = synth.make_reference(600, rng, 0.3)
+    ins = "".join(rng.choice(list("ACGT"), size=9000))
+    cases = [(core, core[:300] + ins + core[300:], "=" * 300 + "I" * 9000 + "=" * 300),
+             (core[:300] + ins + core[300:], core, "=" * 300 + "D" * 9000 + "=" * 300)]
+    eng = engine_factory()
+    _check(eng, cases, _oracle_all(cases, S, NP))
+    assert eng.stats()["overflow_runs"] > 0
+
+
+def test_bad_cigar_is_reported_not_ub(tables, engine_factory):
+    eng = engine_factory()
+    ok = ("ACGTACGT", "ACGTACGT", "8=")
+    bad = ("ACGTACGT", "ACGTACGT", "7=")                                       # consumes 7 of 8 bases
+    refs = [oracle.bases_to_int(c[0]) for c in (ok, bad, ok)]
+    seqs = [oracle.bases_to_int(c[1]) for c in (ok, bad, ok)]
+    outs, _, status = eng.align_many(refs, seqs, [ok[2], bad[2], ok[2]])
+    assert status.tolist() == [0, 16, 0] and outs == ["=" * 8, "", "=" * 8]
+
+
+def test_sub_batching_and_shared_reference_are_invisible(tables):
+    """Same results when the scratch budget forces many sub-batches, and when reads index one shared reference."""
+    from npore_b200.engine import PackedBatch, Realigner, cigar_to_rle, NPORE_OUT_STANDARDIZE, NPORE_OUT_RLE
+    S, NP = tables
+    rng = np.random.default_rng(11)
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(60_000, rng)
+    reads = synth.make_reads(ref, 64, 3000, rng, cm, tracts=tr)
+    refs = [cig.bases_to_int(r[9]) for r in reads]; seqs = [cig.bases_to_int(r[7]) for r in reads]
+    rles = [cigar_to_rle(r[5]) for r in reads]
+    flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE
+    e1 = Realigner(S, NP, max_b_rows=1000)
+    a = e1.align_packed(PackedBatch(refs, seqs, rles, pinned=False), flags)
+    assert e1.stats()["n_sub_batches"] == 1
+    os.environ["NPORE_SCRATCH_MB"] = "4"
+    try:
+        e2 = Realigner(S, NP, max_b_rows=1000)
+    finally:
+        del os.environ["NPORE_SCRATCH_MB"]
+    shared = PackedBatch(None, seqs, rles, shared_ref=cig.bases_to_int(ref), ref_ranges=[(r[3], r[6]) for r in reads], pinned=True)
+    b = e2.align_packed(shared, flags)
+    assert e2.stats()["n_sub_batches"] > 3
+    for k in range(len(reads)):
+        assert a.ops_str(k) == b.ops_str(k) and a.cigar_text(k) == b.cigar_text(k)
+        assert np.array_equal(a.scores(k), b.scores(k))
+    e1.close(); e2.close()
+
+
+def test_full_c2_properties(tables):
+    """BASELINE.json configs[1] at full size (3,000 x 10 kb): size-independent properties of every output --
+    the CIGAR consumes exactly the read and the reference span, '='/'X' agree with the bases, the run is
+    deterministic, and a 64-read sample is bit-exact against the oracle."""
+    import bench
+    from npore_b200.engine import Realigner
+    S, NP = tables
+    _, reads = bench.make_workload(20260101, 1_000_000, 3000, 10_000, NP)
+    packed = bench.pack_reads(reads, pinned=True)
+    eng = Realigner(S, NP)
+    res = eng.align_packed(packed, 0)
+    assert not res.status[:packed.n].any()
+    first = res.ops.copy()
+    chk = 0
+    for k, rd in enumerate(reads):
+        ops = res.ops[res.ops_off[k]:res.ops_off[k + 1]]
+        consumes_ref = int(np.count_nonzero(ops != ord("I"))); consumes_seq = int(np.count_nonzero(ops != ord("D")))
+        assert consumes_ref == len(rd[9]) and consumes_seq == len(rd[7])
+        rpos = np.cumsum(ops != ord("I")) - 1; spos = np.cumsum(ops != ord("D")) - 1
+        diag = (ops == ord("=")) | (ops == ord("X"))
+        rb = np.frombuffer(rd[9].encode(), np.uint8)[rpos[diag]]; sb = np.frombuffer(rd[7].encode(), np.uint8)[spos[diag]]
+        assert np.array_equal(rb == sb, ops[diag] == ord("="))
+        chk ^= hash(ops.tobytes())
+    res2 = eng.align_packed(packed, 0)
+    assert np.array_equal(first[:res.ops_off[packed.n]], res2.ops[:res2.ops_off[packed.n]])          # deterministic
+    for k in range(0, 3000, 47):
+        rd = reads[k]
+        want, wsc, _ = oracle.align(oracle.bases_to_int(rd[9]), oracle.bases_to_int(rd[7]), cig.expand_cigar(rd[5]), S, NP, return_scores=True)
+        assert res.ops_str(k) == want and np.array_equal(res.scores(k), wsc)
+    eng.close()

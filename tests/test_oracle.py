@@ -1,0 +1,99 @@
+"""CPU tests (-m "not gpu"): pin the C oracle (oracle/npore_oracle.c) to the reference's own fixtures.
+
+The golden vectors in tests/golden/ were produced by the UNMODIFIED reference (tests/golden/make_golden.py):
+its one known-answer file test/data/npore_realigned.sam, the get_np_info docstring example (aln.pyx:182-194),
+the inputs of test/align.py and test/get_np_info.py, test/test_std_vcf.vcf, and 400 seeded fuzz cases.
+Where oracle/_ref is built (this container) the oracle is additionally fuzzed live against the reference."""
+import numpy as np
+import pytest
+
+import oracle
+from npore_b200 import synth
+
+
+def test_golden_sam(tables, golden):
+    """bam.pyx:51-89 realign_read on test/data/reads.sam + ref.fasta == test/data/npore_realigned.sam (all 10 records)."""
+    S, NP = tables
+    g = golden("golden_sam.json")
+    assert len(g["reads"]) == 10
+    for rd, want in zip(g["reads"], g["expected_sam"]):
+        read_id, flag, ref_name, start, mapq, cigar, stop, seq, quals, ref, hap = rd
+        cig = oracle.realign_cigar(ref, seq, cigar, S, NP)
+        line = f"{read_id}\t{flag}\t{ref_name}\t{start + 1}\t{mapq}\t{cig}\t*\t0\t{stop - start}\t{seq}\t{quals}\tHP:i:{hap}"
+        assert line == want
+
+
+def test_np_info_kats(golden):
+    for k in golden("np_info_kats.json"):
+        info = oracle.get_np_info(oracle.bases_to_int(k["seq"]))
+        assert info[:, 0, :].T.tolist() == k["L"]
+        assert info[:, 1, :].T.tolist() == k["L_IDX"]
+
+
+def test_np_info_docstring_example():
+    """aln.pyx:182-194."""
+    info = oracle.get_np_info(oracle.bases_to_int("ATATATATTTTTTAAAGCGCGC"))
+    assert info[:, 0, 0].tolist() == [0, 0, 0, 0, 0, 0, 0, 6, 6, 6, 6, 6, 6, 3, 3, 3, 0, 0, 0, 0, 0, 0]
+    assert info[:, 1, 0].tolist() == [0, 0, 0, 0, 0, 0, 0, 0, 1, 2, 3, 4, 5, 0, 1, 2, 0, 0, 0, 0, 0, 0]
+    assert info[:, 0, 1].tolist() == [4, 3, 4, 3, 4, 3, 4, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 0, 3, 0, 3, 0]
+    assert info[:, 1, 1].tolist() == [0, 0, 1, 1, 2, 2, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 2, 0]
+    assert not info[:, :, 2:].any()
+
+
+def test_align_kats(tables, golden):
+    """test/align.py:20-39 cases at (max_b_rows=20, r=10) [test/align.py:59-60] and at align()'s defaults."""
+    S, NP = tables
+    for k in golden("align_kats.json"):
+        ir, iq = oracle.bases_to_int(k["ref"]), oracle.bases_to_int(k["seq"])
+        for tag in ("small", "default"):
+            w = k[tag]
+            out, sc, st = oracle.align(ir, iq, oracle.expand_cigar(k["cigar"]), S, NP, max_b_rows=w["max_b_rows"], r=w["r"],
+                                       return_scores=True)
+            assert out == w["out"] and st == 0
+            assert np.array_equal(sc, np.array(w["scores"], dtype=np.float32))
+
+
+def test_std_vcf_kats(tables, golden):
+    """bam.pyx:93-123 realign_hap on the haplotypes of test/test_std_vcf.vcf."""
+    S, NP = tables
+    for k in golden("std_vcf_kats.json"):
+        ir, iq = oracle.bases_to_int(k["ref"]), oracle.bases_to_int(k["seq"])
+        out = oracle.standardize(oracle.align(ir, iq, oracle.expand_cigar(k["cigar"]), S, NP), ir, iq)
+        assert out == k["out"]
+
+
+def test_fuzz_golden(tables, golden):
+    S, NP = tables
+    for c in golden("fuzz.json.gz"):
+        ir, iq = oracle.bases_to_int(c["ref"]), oracle.bases_to_int(c["seq"])
+        out, sc, st = oracle.align(ir, iq, c["cigar"], S, NP, max_b_rows=c["max_b_rows"], r=c["r"], return_scores=True)
+        assert out == c["out"] and st == 0
+        assert np.array_equal(sc, np.array(c["scores"], dtype=np.float32))
+        assert oracle.collapse_cigar(oracle.standardize(out, ir, iq)) == c["std"]
+
+
+def test_plan_matches_chunk_count(tables):
+    """get_breaks (aln.pyx:344-358): number of chunks and the 'do not split a DI pair' shift."""
+    assert oracle.plan("=" * 30, 30, 30, 20).tolist() == [0, 18, 38, 56, 60]      # breaks at 19k land on 'I' after 'D' -> shifted
+    assert oracle.plan("I" * 5 + "D" * 7, 5, 7, 20000).tolist() == [0, 12]
+    assert len(oracle.plan("", 0, 0, 20)) == 1
+
+
+def test_live_against_reference(tables):
+    """Differential fuzz against the compiled, unmodified reference (only where oracle/_ref is built)."""
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("oracle/_ref not built here")
+    ref = ref_loader.load_reference()
+    S, NP = tables
+    cm = synth.call_length_model(NP)
+    rng = np.random.default_rng(99)
+    for _ in range(150):
+        rf, sq, cg, r, mb = synth.fuzz_case(rng, cm)
+        ir, iq = oracle.bases_to_int(rf), oracle.bases_to_int(sq)
+        want, wsc = ref.aln_sc.align(ir, iq, cg, S, NP, 5, 1, mb, r)
+        got, gsc, st = oracle.align(ir, iq, cg, S, NP, max_b_rows=mb, r=r, return_scores=True)
+        assert got == want and st == 0
+        assert np.array_equal(gsc, np.array(wsc, dtype=np.float32))
+        if len(ir):
+            assert np.array_equal(np.asarray(ref.aln.get_np_info(ir)), oracle.get_np_info(ir))
