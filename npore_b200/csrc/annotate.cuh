@@ -12,11 +12,19 @@
 //            sequential overwrite rules can depend on (incl. the max_l clamp quirk).
 // raw[p][n-1] = L | 0x80 if L_IDX == 0.
 //
-// Records (one per slice position, "relaid" so that the record at column j holds what cell (.,j) gathers):
-//   colrec[j] (uint2):  .x = raw[j-n][n] for n=1..4 (one byte each);
-//                       .y = raw[j-5][5] | raw[j-6][6]<<8 | SHRmask<<16 | LENmask<<22 | base(ref[j-1])<<28
-//                       SHRmask bit n-1 = (raw[j-n][n] & 0x7f) != 0 ; LENmask bit n-1 = raw[j][n] has L!=0 && L_IDX==0
-//   rowrec[i] (uint32): bits 0-5  = (raw_seq[i-n][n] & 0x7f) != 0 ; bits 8-13 = L_IDX(seq)[i-n][n]==0 ; bits 16-18 = seq[i-1]
+// Records (one per slice position), pre-decoded for the forward kernel (forward.cuh):
+//   relaid[j] (uint2): .x = raw[j-n][n] for n=1..4 (one byte each); .y = raw[j-5][5] | raw[j-6][6]<<8 |
+//                      LENmask<<22 (bit n-1: raw[j][n] has L!=0 && L_IDX==0).  "Relaid" = the record of column j
+//                      holds what the SHR gather of a cell in column j needs from columns j-1..j-6.  Only the
+//                      rare generic path of the forward kernel reads it.
+//   colrec[j] (uint4): .x/.y = the first two SHR candidate descriptors of column j, period n descending (0 = none):
+//                        [0:2] n  [3] source is a tract start (L_IDX==0)  [4:10] L  [11:18] ring slot of the source
+//                        column (j-n) & (NC-1)  [19:28] score-table row (n-1)*T + min(L, clamp)
+//                      .z = [0:2] base ref[j-1]  [3] more than two SHR candidates  [4] more than one LEN-eligible n
+//                           [5] k-mer contains N  [6:17] 2-bit k-mer ref[j..j+5]
+//                      .w = LEN descriptor of the single LEN-eligible period at j: [0:2] n  [4:10] L  [19:28] table row
+//   rowrec[i] (uint32): [0:5] tract present at i-n  [6:11] tract start at i-n (L_IDX==0)  [12:14] base seq[i-1]
+//                       [15] k-mer contains N  [16:27] 2-bit k-mer seq[i..i+5]
 #pragma once
 #include "common.cuh"
 
@@ -31,8 +39,8 @@ struct AnnotateArgs {
     const uint8_t *ref_codes, *seq_codes;
     uint8_t *raw_ref, *raw_seq;    // 8 B per entry
     int32_t *nf_ref, *lf_ref, *nf_seq, *lf_seq;
-    uint2 *colrec; uint32_t *rowrec;
-    int max_n, max_l;
+    uint4 *colrec; uint2 *relaid; uint32_t *rowrec;
+    int max_n, max_l, nc, np_dim, np_clamp;
 };
 
 // np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
@@ -121,6 +129,19 @@ __device__ __forceinline__ uint32_t raw_byte(const uint8_t *raw, int len, int p,
     return (p >= 0 && p < len) ? (uint32_t)raw[(size_t)p * 8 + n - 1] : 0u;
 }
 
+__device__ __forceinline__ uint32_t kmer2_of(const uint8_t *s, int len, int p, uint32_t &hasN)
+{
+    uint32_t km = 0;
+#pragma unroll
+    for (int t = 0; t < 6; t++) {
+        const int q = p + t;
+        uint32_t b = 0;
+        if (q >= 0 && q < len) { b = s[q]; if (b == 0 || b > 4) hasN = 1; }
+        km |= ((b - 1u) & 3u) << (2 * t);
+    }
+    return km;
+}
+
 __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
 {
     const int ci = blockIdx.x >> 1, side = blockIdx.x & 1;
@@ -134,23 +155,41 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         const uint8_t *s = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
         uint8_t *raw = a.raw_ref + sl.col_off * 8;
         annotate_slice(s, len, a.max_n, a.max_l, raw, a.nf_ref + sl.col_off, a.lf_ref + sl.col_off, nullptr);
-        uint2 *out = a.colrec + sl.col_off;
+        uint4 *out = a.colrec + sl.col_off;
+        uint2 *rel = a.relaid + sl.col_off;
         for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
             uint2 v = make_uint2(0u, 0u);
+            uint4 w = make_uint4(0u, 0u, 0u, 0u);
             if (j < len + 8) {
-                uint32_t shr = 0, lenm = 0;
+                uint32_t lenm = 0, nshr = 0, nlen = 0;
 #pragma unroll
-                for (int n = 1; n <= NP_MAXN; n++) {
+                for (int n = NP_MAXN; n >= 1; n--) {
                     const uint32_t b = raw_byte(raw, len, j - n, n);
                     if (n <= 4) v.x |= b << (8 * (n - 1)); else v.y |= b << (8 * (n - 5));
-                    if (b & 0x7fu) shr |= 1u << (n - 1);
+                    const uint32_t L = b & 0x7fu;
+                    if (L) {
+                        const uint32_t d = (uint32_t)n | ((b >> 7) << 3) | (L << 4) | ((uint32_t)((j - n) & (a.nc - 1)) << 11) |
+                                           ((uint32_t)((n - 1) * a.np_dim + min((int)L, a.np_clamp)) << 19);
+                        if (nshr == 0) w.x = d; else if (nshr == 1) w.y = d;
+                        nshr++;
+                    }
                     const uint32_t o = raw_byte(raw, len, j, n);
-                    if ((o & 0x7fu) && (o & 0x80u)) lenm |= 1u << (n - 1);
+                    if ((o & 0x7fu) && (o & 0x80u)) {
+                        lenm |= 1u << (n - 1);
+                        const uint32_t Lo = o & 0x7fu;
+                        w.w = (uint32_t)n | (Lo << 4) | ((uint32_t)((n - 1) * a.np_dim + min((int)Lo, a.np_clamp)) << 19);
+                        nlen++;
+                    }
                 }
+                v.y |= lenm << 22;
                 const uint32_t base = (j >= 1 && j - 1 < len) ? s[j - 1] : 0u;
-                v.y |= shr << 16 | lenm << 22 | (base & 7u) << 28;
+                uint32_t hasN = 0;
+                const uint32_t km = kmer2_of(s, len, j, hasN);
+                if (nlen > 1) w.w = 0;
+                w.z = (base & 7u) | (nshr > 2 ? 8u : 0u) | (nlen > 1 ? 16u : 0u) | (hasN << 5) | (km << 6);
             }
-            out[j] = v;
+            out[j] = w;
+            rel[j] = v;
         }
     } else {
         const int len = c.slen;
@@ -165,10 +204,12 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                 for (int n = 1; n <= NP_MAXN; n++) {
                     const uint32_t b = raw_byte(raw, len, i - n, n);
                     if (b & 0x7fu) v |= 1u << (n - 1);
-                    if (b & 0x80u) v |= 1u << (8 + n - 1);
+                    if (b & 0x80u) v |= 1u << (6 + n - 1);
                 }
                 const uint32_t base = (i >= 1 && i - 1 < len) ? s[i - 1] : 0u;
-                v |= (base & 7u) << 16;
+                uint32_t hasN = 0;
+                const uint32_t km = kmer2_of(s, len, i, hasN);
+                v |= (base & 7u) << 12 | hasN << 15 | km << 16;
             }
             out[i] = v;
         }

@@ -73,7 +73,7 @@ struct npore_ctx {
     DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
         d_item_len, d_item_status, d_rle_out, d_rle_len, d_order, d_slots, d_counter, d_ovf, d_ovf_count;
     // per sub-batch scratch
-    DevBuf d_colrec, d_rowrec, d_raw_ref, d_raw_seq, d_nf_ref, d_lf_ref, d_nf_seq, d_lf_seq, d_tb;
+    DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_nf_ref, d_lf_ref, d_nf_seq, d_lf_seq, d_tb;
     HostBuf h_ops, h_rle, h_small;
     std::vector<ItemDesc> items;
     std::vector<int32_t> order;
@@ -162,6 +162,7 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     if (max_l < 1 || max_l > 127 || np_dim < max_l) return NPORE_ERR_BAD_ARG;   // L must fit 7 bits; index clamp is max_l-1
     if (max_b_rows < 2 || max_b_rows > 65000) return NPORE_ERR_BAD_ARG;          // runs are carried in 16 bits
     if (r < 1 || 2 * r + 1 > 32 * 8) return NPORE_ERR_BAD_ARG;
+    if ((int64_t)np_n * np_dim > 1023) return NPORE_ERR_BAD_ARG;                 // score-table row index is a 10-bit descriptor field
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return NPORE_ERR_NO_DEVICE; }
     if (device < 0 || device >= ndev) return NPORE_ERR_BAD_ARG;
@@ -190,6 +191,8 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
         ctx->d_ovf.ensure(sizeof(OverflowRec) * npore_ctx::OVF_CAP) != cudaSuccess) return bail(NPORE_ERR_OOM);
     size_t fr = 0, tot = 0;
     cudaMemGetInfo(&fr, &tot);
+    fwd_init_constants();
+    if (cudaGetLastError() != cudaSuccess) return bail(NPORE_ERR_CUDA);
     ctx->scratch_budget = (size_t)((double)fr * 0.55);
     if (const char *s = getenv("NPORE_SCRATCH_MB")) ctx->scratch_budget = (size_t)atoll(s) << 20;
     *out = ctx;
@@ -203,7 +206,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
                       &ctx->d_item_status, &ctx->d_rle_out, &ctx->d_rle_len, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
-                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq,
+                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq,
                       &ctx->d_nf_ref, &ctx->d_lf_ref, &ctx->d_nf_seq, &ctx->d_lf_seq, &ctx->d_tb};
     for (auto *b : bufs) b->release();
     ctx->h_ops.release(); ctx->h_rle.release(); ctx->h_small.release();
@@ -339,7 +342,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     ctx->subs.clear();
     size_t max_col = 0, max_row = 0, max_tb = 0;
     {
-        const size_t per_entry = 8 + 8 + 4 + 4 + 4 + 8 + 4 + 4;   // colrec, raw_ref, nf/lf ref, rowrec, raw_seq, nf/lf seq
+        const size_t per_entry = 16 + 8 + 8 + 4 + 4 + 4 + 8 + 4 + 4;   // colrec, relaid, raw_ref, nf/lf ref, rowrec, raw_seq, nf/lf seq
         size_t col = 0, row = 0, tb = 0; int first = 0;
         for (int64_t k = 0; k < nchunks; k++) {
             const int bm = ctx->chunk_bmax[ctx->order[k]];
@@ -360,7 +363,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
             max_col = std::max(max_col, col); max_row = std::max(max_row, row); max_tb = std::max(max_tb, tb);
         }
     }
-    CU(ctx->d_colrec.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
+    CU(ctx->d_colrec.ensure(max_col * 16 + 64)); CU(ctx->d_relaid.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
     CU(ctx->d_nf_ref.ensure(max_col * 4 + 64)); CU(ctx->d_lf_ref.ensure(max_col * 4 + 64));
     CU(ctx->d_rowrec.ensure(max_row * 4 + 64)); CU(ctx->d_raw_seq.ensure(max_row * 8 + 64));
     CU(ctx->d_nf_seq.ensure(max_row * 4 + 64)); CU(ctx->d_lf_seq.ensure(max_row * 4 + 64));
@@ -391,8 +394,8 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         aa.raw_ref = ctx->d_raw_ref.as<uint8_t>(); aa.raw_seq = ctx->d_raw_seq.as<uint8_t>();
         aa.nf_ref = ctx->d_nf_ref.as<int32_t>(); aa.lf_ref = ctx->d_lf_ref.as<int32_t>();
         aa.nf_seq = ctx->d_nf_seq.as<int32_t>(); aa.lf_seq = ctx->d_lf_seq.as<int32_t>();
-        aa.colrec = ctx->d_colrec.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
-        aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l;
+        aa.colrec = ctx->d_colrec.as<uint4>(); aa.relaid = ctx->d_relaid.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
+        aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.np_dim = ctx->P.np_dim; aa.np_clamp = ctx->P.np_clamp;
         CU(cudaEventRecord(e0, ctx->stream));
         annotate_kernel<<<2 * sb.count, ANN_THREADS, 0, ctx->stream>>>(aa);
         CU(cudaGetLastError()); S.launches++;
@@ -401,7 +404,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         ForwardArgs fa{};
         fa.chunks = aa.chunks; fa.slots = aa.slots; fa.order = aa.order; fa.n = sb.count;
         fa.counter = ctx->d_counter.as<int>(); fa.items = aa.items; fa.bits = ctx->d_bits.as<uint32_t>();
-        fa.ref_codes = aa.ref_codes; fa.seq_codes = aa.seq_codes; fa.colrec = aa.colrec; fa.rowrec = aa.rowrec;
+        fa.ref_codes = aa.ref_codes; fa.seq_codes = aa.seq_codes; fa.colrec = aa.colrec; fa.relaid = aa.relaid; fa.rowrec = aa.rowrec;
         fa.tb = ctx->d_tb.as<uint16_t>(); fa.np_tab = ctx->d_np.as<float>(); fa.sub_tab = ctx->d_sub.as<float>();
         fa.out = ctx->d_chunk_out.as<ChunkOut>();
         fa.ovf = ctx->d_ovf.as<OverflowRec>(); fa.ovf_count = ctx->d_ovf_count.as<int>(); fa.ovf_cap = npore_ctx::OVF_CAP;

@@ -34,7 +34,6 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
     if (!c.valid) { ChunkOut o; o.score = 0.f; o.status = 0; o.start = 0; o.len = 0; a.out[cid] = o; return; }
     const ChunkSlot sl = a.slots[idx];
     const ItemDesc &I = a.items[c.item];
-    const uint32_t *bits = a.bits + I.bit_word_off, *cum = a.cum + I.bit_word_off;
     const uint8_t *refs = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
     const uint8_t *seqs = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
     const uint16_t *tb = a.tb + (size_t)sl.tb_off * (32 * a.tbs);
@@ -44,11 +43,10 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
     while (i > 0 || j > 0) {
         if (i < 0) { status = 1; break; }
         if (j < 0) { status = 2; break; }
-        const int d = i + j, g = c.brk + d;
-        const int Id = (int)(cum[g >> 5] + __popc(bits[g >> 5] & ((1u << (g & 31)) - 1u))) - c.r0;
-        const int bc = Id + a.r - i;
+        // records are stored per anti-diagonal in slot order: slot = column index mod NC (forward.cuh)
+        const int d = i + j, bc = j & (32 * a.cpl - 1);
         uint32_t rec = 0;
-        if (bc >= 0 && bc < a.W && d < c.B) rec = tb[(size_t)d * (32 * a.tbs) + (bc / a.cpl) * a.tbs + (bc % a.cpl)];
+        if (d < c.B) rec = tb[(size_t)d * (32 * a.tbs) + (bc / a.cpl) * a.tbs + (bc % a.cpl)];
         const int typ = (int)(rec & 7u);
         int run = (int)(rec >> 3);
         if (typ != T_MAT && run == NP_RUN_SAT) {
