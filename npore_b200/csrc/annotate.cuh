@@ -18,13 +18,14 @@
 //                      holds what the SHR gather of a cell in column j needs from columns j-1..j-6.  Only the
 //                      rare generic path of the forward kernel reads it.
 //   colrec[j] (uint4): .x/.y = the first two SHR candidate descriptors of column j, period n descending (0 = none):
-//                        [0:2] n  [3] source is a tract start (L_IDX==0)  [4:10] L  [11:18] ring slot of the source
-//                        column (j-n) & (NC-1)  [19:28] score-table row (n-1)*T + min(L, clamp)
-//                      .z = [0:2] base ref[j-1]  [3] more than two SHR candidates  [4] more than one LEN-eligible n
-//                           [5] k-mer contains N  [6:17] 2-bit k-mer ref[j..j+5]
-//                      .w = LEN descriptor of the single LEN-eligible period at j: [0:2] n  [4:10] L  [19:28] table row
-//   rowrec[i] (uint32): [0:5] tract present at i-n  [6:11] tract start at i-n (L_IDX==0)  [12:14] base seq[i-1]
-//                       [15] k-mer contains N  [16:27] 2-bit k-mer seq[i..i+5]
+//                        [2:4] n  [5:11] L  [19:31] (byte offset of the source cell in the forward kernel's history ring)>>2
+//                        = ring row (-n mod 8), array (0 = MAT value if the source column starts the tract, L_IDX==0;
+//                        1 = carried SHR run-start value otherwise), slot (j-n) mod NC          (see forward.cuh)
+//                      .z = [0] generic path (more than two SHR candidates or more than one LEN-eligible period; then
+//                           .x/.y/.w are 0)  [1] k-mer contains N  [2:4] base ref[j-1]  [20:31] 2-bit k-mer ref[j..j+5]
+//                      .w = LEN descriptor of the single LEN-eligible period at j: [2:4] n  [5:11] L  [19:31] ring row offset>>2
+//   rowrec[i] (uint32): [1:6] tract present at i-n (bit n)  [7:12] tract start at i-n (bit 6+n)  [15] k-mer contains N
+//                       [16:18] base seq[i-1]  [20:31] 2-bit k-mer seq[i..i+5]
 #pragma once
 #include "common.cuh"
 
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         annotate_slice(s, len, a.max_n, a.max_l, raw, a.nf_ref + sl.col_off, a.lf_ref + sl.col_off, nullptr);
         uint4 *out = a.colrec + sl.col_off;
         uint2 *rel = a.relaid + sl.col_off;
+        const int NC = a.nc;
         for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
             uint2 v = make_uint2(0u, 0u);
             uint4 w = make_uint4(0u, 0u, 0u, 0u);
@@ -168,16 +170,18 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                     if (n <= 4) v.x |= b << (8 * (n - 1)); else v.y |= b << (8 * (n - 5));
                     const uint32_t L = b & 0x7fu;
                     if (L) {
-                        const uint32_t d = (uint32_t)n | ((b >> 7) << 3) | (L << 4) | ((uint32_t)((j - n) & (a.nc - 1)) << 11) |
-                                           ((uint32_t)((n - 1) * a.np_dim + min((int)L, a.np_clamp)) << 19);
+                        // byte offset inside one warp's ring [NP_RING][4 arrays][NC] floats
+                        const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + ((b & 0x80u) ? 0u : (uint32_t)(NC * 4)) +
+                                           (uint32_t)((j - n) & (NC - 1)) * 4u;
+                        const uint32_t d = ((uint32_t)n << 2) | (L << 5) | ((F >> 2) << 19);
                         if (nshr == 0) w.x = d; else if (nshr == 1) w.y = d;
                         nshr++;
                     }
                     const uint32_t o = raw_byte(raw, len, j, n);
                     if ((o & 0x7fu) && (o & 0x80u)) {
                         lenm |= 1u << (n - 1);
-                        const uint32_t Lo = o & 0x7fu;
-                        w.w = (uint32_t)n | (Lo << 4) | ((uint32_t)((n - 1) * a.np_dim + min((int)Lo, a.np_clamp)) << 19);
+                        const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16);
+                        w.w = ((uint32_t)n << 2) | ((o & 0x7fu) << 5) | ((F >> 2) << 19);
                         nlen++;
                     }
                 }
@@ -185,8 +189,9 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                 const uint32_t base = (j >= 1 && j - 1 < len) ? s[j - 1] : 0u;
                 uint32_t hasN = 0;
                 const uint32_t km = kmer2_of(s, len, j, hasN);
-                if (nlen > 1) w.w = 0;
-                w.z = (base & 7u) | (nshr > 2 ? 8u : 0u) | (nlen > 1 ? 16u : 0u) | (hasN << 5) | (km << 6);
+                const bool more = nshr > 2 || nlen > 1;
+                if (more) { w.x = w.y = w.w = 0u; }
+                w.z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (km << 20);
             }
             out[j] = w;
             rel[j] = v;
@@ -203,13 +208,13 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
 #pragma unroll
                 for (int n = 1; n <= NP_MAXN; n++) {
                     const uint32_t b = raw_byte(raw, len, i - n, n);
-                    if (b & 0x7fu) v |= 1u << (n - 1);
-                    if (b & 0x80u) v |= 1u << (6 + n - 1);
+                    if (b & 0x7fu) v |= 1u << n;
+                    if (b & 0x80u) v |= 1u << (6 + n);
                 }
                 const uint32_t base = (i >= 1 && i - 1 < len) ? s[i - 1] : 0u;
                 uint32_t hasN = 0;
                 const uint32_t km = kmer2_of(s, len, i, hasN);
-                v |= (base & 7u) << 12 | hasN << 15 | km << 16;
+                v |= hasN << 15 | (base & 7u) << 16 | km << 20;
             }
             out[i] = v;
         }

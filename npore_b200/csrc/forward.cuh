@@ -64,25 +64,42 @@ static void fwd_init_constants()
     cudaMemcpyToSymbol(c_sipack, h, sizeof(h));
 }
 
-// One SHR candidate from a pre-decoded descriptor (aln.pyx:642-667 in gather form).
+// ---- explicit shared-memory access by 32-bit byte address (keeps address arithmetic to what is written here)
+__device__ __forceinline__ float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+template <int OFF> __device__ __forceinline__ uint32_t lds_u_off(uint32_t a)
+{ uint32_t v; asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF)); return v; }
+__device__ __forceinline__ uint2 lds_u2(uint32_t a)
+{ uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+template <int OFF> __device__ __forceinline__ void sts_f_off(uint32_t a, float v)
+{ asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "f"(v) : "memory"); }
+template <int OFF> __device__ __forceinline__ void sts_u_off(uint32_t a, uint32_t v)
+{ asm volatile("st.shared.u32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "r"(v) : "memory"); }
+
+// History ring of one warp: float ring[NP_RING][4][NC]   (arrays: 0 MAT.VAL, 1 SHR run-start value, 2 LEN run-start
+// value, 3 LEN.RUN | SHR.RUN<<16), NC*128 bytes, aligned to its size so that (offset & mask) | base addresses it.
+// One SHR candidate from a pre-decoded descriptor (aln.pyx:642-667 in gather form; annotate.cuh for the fields).
 template <int NC>
-__device__ __forceinline__ void shr_eval(uint32_t D, bool pred, int d, int bc, uint32_t sip, const float *rgM,
-                                         const uint32_t *rgR, const uint32_t *s_magic, const float *__restrict__ np, int T, int cl,
-                                         float &Sv, int &Sr, float &Sb)
+__device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, uint32_t wbase, uint32_t lutbase, int bc, uint32_t sip,
+                                         const float *__restrict__ np, int T, int cl, float &Sv, int &Sr, float &Sb)
 {
     if (pred) {
-        const int n = (int)(D & 7u);
-        const bool start = (D & 8u) != 0u;
-        const int at = ((d - n) & (NP_RING - 1)) * NC + (int)((D >> 11) & 0xffu);
-        const float base = rgM[at + (start ? 0 : NP_RING * NC)];          // rgS follows rgM
-        const int run0 = start ? 0 : (int)(rgR[at] >> 16);
-        const bool ok = (bc > (int)((sip >> (4 * n)) & 7u)) && (start || run0 > 0);
-        const int q = (int)__umulhi((uint32_t)run0 << 1, s_magic[n]);
-        const int call = (int)((D >> 4) & 0x7fu) - q - 1;
+        const uint32_t f = (D >> 17) + dsh;
+        const uint32_t a = (f & (uint32_t)(NC * 128 - 4)) | wbase;
+        const float base = lds_f(a);
+        const uint32_t rr = lds_u_off<NC * 8>(a);                         // array + 2: run word when base is array 1
+        const uint32_t n4 = D & 0x1cu;
+        const uint2 lut = lds_u2(lutbase + n4 * 2u);                      // {ceil(2^31/n), (n-1)*T*T}
+        const bool start = (D & ((uint32_t)NC << 19)) == 0u;              // array bit of the descriptor offset field
+        const int run0 = start ? 0 : (int)(rr >> 16);
+        const bool ok = (bc > (int)((sip >> n4) & 7u)) && (start || run0 > 0);
+        const int q = (int)__umulhi((uint32_t)run0 << 1, lut.x);
+        const int L = (int)((D >> 5) & 0x7fu);
+        const int call = L - q - 1;
+        const uint32_t idx = lut.y + (uint32_t)(min(L, cl) * T) + (uint32_t)min(call, cl);
         float sc = 100.f;
-        if (call >= 0) sc = __ldg(np + (int)(D >> 19) * T + min(call, cl));
+        if (call >= 0) sc = __ldg(np + idx);
         const float cand = base + sc;
-        if (ok && cand < Sv) { Sv = cand; Sr = run0 + n; Sb = base; }
+        if (ok && cand < Sv) { Sv = cand; Sr = run0 + (int)(n4 >> 2); Sb = base; }
     }
 }
 
@@ -91,25 +108,29 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
 {
     constexpr int NC = 32 * CPL;
     constexpr int TBS = CPL <= 1 ? 1 : CPL <= 2 ? 2 : CPL <= 4 ? 4 : 8;
+    constexpr uint32_t RING_BYTES = NC * 128;                    // per warp
     extern __shared__ float smem[];
     __shared__ float s_sub[64];
-    __shared__ uint32_t s_magic[8];
+    __shared__ uint2 s_lut[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) {
         const int sb = threadIdx.x >> 3, rb = threadIdx.x & 7;
         s_sub[threadIdx.x] = (sb < 5 && rb < 5) ? a.sub_tab[sb * 5 + rb] : 0.f;
     }
-    if (threadIdx.x < 8) s_magic[threadIdx.x] = threadIdx.x >= 1 ? (uint32_t)((0x80000000ull + threadIdx.x - 1) / threadIdx.x) : 0u;
+    if (threadIdx.x < 8) {
+        const uint32_t n = threadIdx.x;
+        s_lut[n] = make_uint2(n >= 1 ? (uint32_t)((0x80000000ull + n - 1) / n) : 0u, n >= 1 ? (n - 1) * a.P.np_dim * a.P.np_dim : 0u);
+    }
     __syncthreads();
-
-    float *rgM = smem + (size_t)warp * 4 * NP_RING * NC;       // MAT.VAL            [ring][slot]
-    float *rgS = rgM + NP_RING * NC;                             // SHR run-start value (must follow rgM)
-    float *rgL = rgS + NP_RING * NC;                             // LEN run-start value
-    uint32_t *rgR = reinterpret_cast<uint32_t *>(rgL + NP_RING * NC);   // LEN.RUN | SHR.RUN << 16
+    const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem) + RING_BYTES - 1u) & ~(RING_BYTES - 1u);
+    const uint32_t wbase = smem_base + (uint32_t)warp * RING_BYTES;
+    const uint32_t subbase = (uint32_t)__cvta_generic_to_shared(s_sub);
+    const uint32_t lutbase = (uint32_t)__cvta_generic_to_shared(s_lut);
+    const uint32_t myslot4 = (uint32_t)(lane * CPL) * 4u;
 
     const int r = a.P.r, T = a.P.np_dim, cl = a.P.np_clamp;
     const float gopen = a.P.gap_open, gext = a.P.gap_ext;
-    const uint32_t nmask = (1u << a.P.max_n) - 1u;
+    const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 1;       // rowrec "present" bits live at [1:6]
     const float *__restrict__ np = a.np_tab;
     const int src_lane = (lane + 31) & 31;
 
@@ -147,21 +168,25 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             if (j0 == 0) cc[k] = col[0];
         }
         uint32_t nrow = row[r + 1];                          // next row to enter the band (at b_col == 0)
-        int wbase = c.brk >> 5; uint32_t wbuf = bits[wbase + lane];
+        int wbase_w = c.brk >> 5; uint32_t wbuf = bits[wbase_w + lane];
         uint32_t cw = __shfl_sync(NP_FULL, wbuf, 0);
         uint32_t hist = 0; int Id = 0, Dd = 0;
+        float infd = 0.f;                                     // 100*d, exact in fp32 (d < 2^16)
+        // steady state = every cell with 1 <= b_col <= 2r-1 is an interior cell with i >= 2 and j >= 2
+        const int idLo = r + 1, idSpan = imax - 2 * r, ddSpan = jmax - 2 * r;
 
         for (int d = 0; d < B; d++) {
             float lMv[CPL], lDv[CPL]; int lDM[CPL];
             if (d > 0) {
                 const int g = c.brk + d - 1;                 // op that leads to this anti-diagonal
                 if ((g & 31) == 0 && d > 1) {
-                    int wi = (g >> 5) - wbase;
-                    if (wi >= 32) { wbase += 32; wbuf = bits[wbase + lane]; wi -= 32; }
+                    int wi = (g >> 5) - wbase_w;
+                    if (wi >= 32) { wbase_w += 32; wbuf = bits[wbase_w + lane]; wi -= 32; }
                     cw = __shfl_sync(NP_FULL, wbuf, wi);
                 }
                 const uint32_t o = (cw >> (g & 31)) & 1u;
                 hist = ((hist << 1) | o) & 0x3fu;
+                infd += 100.f;
                 const float a0 = __shfl_sync(NP_FULL, Mv1[CPL - 1], src_lane);
                 const float a1 = __shfl_sync(NP_FULL, Dv1[CPL - 1], src_lane);
                 const int a2 = __shfl_sync(NP_FULL, DM1[CPL - 1], src_lane);
@@ -190,37 +215,37 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
 #pragma unroll
                 for (int k = 0; k < CPL; k++) { lMv[k] = lDv[k] = 0.f; lDM[k] = 0; }
             }
-            const int jlo = Dd - r;
             const uint32_t sip = c_sipack[hist];
-            const float infd = (float)(100 * d), edgev = (float)(100 * (d + 1));
-            // interior-cell bounds on b_col for this anti-diagonal (aln.pyx:497-507)
-            const int lo = max(1, max(Id + r - imax, r - Dd)), hi = min(2 * r - 1, min(Id + r, jmax + r - Dd));
-            const bool steady = (Id > r) && (Dd > r) && (Id <= imax - r + 1) && (Dd <= jmax - r + 1);
+            const float edgev = infd + 100.f;
+            const uint32_t dsh = (uint32_t)d * (uint32_t)(NC * 16);
+            const bool steady = (unsigned)(Id - idLo) <= (unsigned)idSpan && (unsigned)(Dd - idLo) <= (unsigned)ddSpan && idSpan >= 0 && ddSpan >= 0;
+            int lo = 1, hi = 2 * r - 1;
+            if (!steady) {      // interior-cell bounds on b_col for this anti-diagonal (aln.pyx:497-507)
+                lo = max(1, max(Id + r - imax, r - Dd)); hi = min(2 * r - 1, min(Id + r, jmax + r - Dd));
+                if (hi < lo) { lo = 1; hi = 0; }
+            }
+            const unsigned span = (unsigned)(hi - lo);
 
             bool in[CPL];
             float Sv[CPL], Sb[CPL], Lv[CPL], Lb[CPL]; int Sr[CPL], Lr[CPL];
             bool p0[CPL], p1[CPL], pg[CPL], pl[CPL];
-            bool any0 = false, any1 = false, anyg = false, anyl = false;
+            bool any1 = false, anyg = false, anyl = false;
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
-                in[k] = (unsigned)(bc[k] - lo) <= (unsigned)(hi - lo) && hi >= lo;
+                in[k] = (unsigned)(bc[k] - lo) <= span && hi >= lo;
                 Sv[k] = infd; Lv[k] = infd; Sb[k] = 0.f; Lb[k] = 0.f; Sr[k] = 0; Lr[k] = 0;
-                const bool more = (cc[k].z & 24u) != 0u;          // >2 SHR candidates or >1 LEN-eligible period: generic path
-                p0[k] = in[k] && !more && cc[k].x != 0u;
-                p1[k] = in[k] && !more && cc[k].y != 0u;
-                pg[k] = in[k] && more;
-                const uint32_t ln = cc[k].w & 7u;
-                pl[k] = in[k] && !more && ln != 0u && (((rw[k] << 1) >> ln) & 1u);
-                any0 |= p0[k]; any1 |= p1[k]; anyg |= pg[k]; anyl |= pl[k];
+                p0[k] = in[k] && cc[k].x != 0u;
+                p1[k] = in[k] && cc[k].y != 0u;
+                pg[k] = in[k] && (cc[k].z & 1u);
+                pl[k] = in[k] && (((rw[k] & nmask) >> ((cc[k].w >> 2) & 7u)) & 1u);   // rowrec bit 0 is always 0
+                any1 |= p1[k]; anyg |= pg[k]; anyl |= pl[k];
             }
-            // ---- SHR gather: descriptor 0 (largest period), then descriptor 1
-            if (__any_sync(NP_FULL, any0)) {
+            // ---- SHR gather: descriptor 0 (largest period; some lane almost always has one), then descriptor 1
 #pragma unroll
-                for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].x, p0[k], d, bc[k], sip, rgM, rgR, s_magic, np, T, cl, Sv[k], Sr[k], Sb[k]);
-            }
+            for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].x, p0[k], dsh, wbase, lutbase, bc[k], sip, np, T, cl, Sv[k], Sr[k], Sb[k]);
             if (__any_sync(NP_FULL, any1)) {
 #pragma unroll
-                for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].y, p1[k], d, bc[k], sip, rgM, rgR, s_magic, np, T, cl, Sv[k], Sr[k], Sb[k]);
+                for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].y, p1[k], dsh, wbase, lutbase, bc[k], sip, np, T, cl, Sv[k], Sr[k], Sb[k]);
             }
             // ---- LEN gather (aln.pyx:602-633): single eligible period, 2-bit k-mer unit compare in registers
             if (__any_sync(NP_FULL, anyl)) {
@@ -228,20 +253,24 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 for (int k = 0; k < CPL; k++) {
                     if (pl[k]) {
                         const uint32_t D = cc[k].w;
-                        const int n = (int)(D & 7u);
-                        if (((cc[k].z >> 5) | (rw[k] >> 15)) & 1u) {
+                        if ((cc[k].z | (rw[k] >> 14)) & 2u) {
                             pg[k] = true; anyg = true;             // an N inside a k-mer: byte-wise compare on the generic path
                         } else {
-                            const bool eq = ((((cc[k].z >> 6) ^ (rw[k] >> 16)) & ((1u << (2 * n)) - 1u)) == 0u);
-                            const int sI = (int)((sip >> (4 * n)) & 7u);
-                            const bool start = ((rw[k] >> (6 + n - 1)) & 1u) != 0u;
-                            const int at = ((d - n) & (NP_RING - 1)) * NC + lane * CPL + k;
-                            const float base = start ? rgM[at] : rgL[at];
-                            const int run0 = start ? 0 : (int)(rgR[at] & 0xffffu);
-                            const bool ok = eq && (bc[k] + n - sI <= 2 * r - 1) && (start || run0 > 0);
-                            const int q = (int)__umulhi((uint32_t)run0 << 1, s_magic[n]);
-                            const int call = (int)((D >> 4) & 0x7fu) + q + 1;
-                            const float cand = base + __ldg(np + (int)(D >> 19) * T + min(call, cl));
+                            const uint32_t n4 = D & 0x1cu;
+                            const int n = (int)(n4 >> 2);
+                            const bool eq = (((cc[k].z ^ rw[k]) >> 20) << (32 - 2 * n)) == 0u;
+                            const bool start = ((rw[k] >> (6 + n)) & 1u) != 0u;
+                            const uint32_t f = (D >> 17) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
+                            const uint32_t ad = (f & (uint32_t)(NC * 128 - 4)) | wbase;
+                            const float base = lds_f(ad);
+                            const uint32_t rr = lds_u_off<NC * 4>(ad);                 // array 2 + 1 = run word
+                            const uint2 lut = lds_u2(lutbase + n4 * 2u);
+                            const int run0 = start ? 0 : (int)(rr & 0xffffu);
+                            const bool ok = eq && (bc[k] + n - (int)((sip >> n4) & 7u) <= 2 * r - 1) && (start || run0 > 0);
+                            const int q = (int)__umulhi((uint32_t)run0 << 1, lut.x);
+                            const int L = (int)((D >> 5) & 0x7fu);
+                            const int call = L + q + 1;
+                            const float cand = base + __ldg(np + (lut.y + (uint32_t)(min(L, cl) * T) + (uint32_t)min(call, cl)));
                             if (ok && cand < Lv[k]) { Lv[k] = cand; Lr[k] = run0 + n; Lb[k] = base; }
                         }
                     }
@@ -252,20 +281,20 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
                     if (pg[k]) {
-                        const int i = Id + r - bc[k], j = jlo + bc[k];
+                        const int i = Id + r - bc[k], j = Dd - r + bc[k];
                         const uint2 rb = rel[j];
-                        const bool more = (cc[k].z & 24u) != 0u;
-                        if (more) {
+                        if (cc[k].z & 1u) {
                             for (int n = a.P.max_n; n >= 1; n--) {      // SHR, every period
                                 const uint32_t byte = ((n <= 4 ? rb.x : rb.y) >> ((8 * (n - 1)) & 31)) & 0xffu;
-                                const int L = (int)(byte & 0x7fu);
+                                const uint32_t L = byte & 0x7fu;
                                 if (!L) continue;
-                                const uint32_t D = (uint32_t)n | ((byte >> 7) << 3) | ((uint32_t)L << 4) |
-                                                   ((uint32_t)((j - n) & (NC - 1)) << 11) | ((uint32_t)((n - 1) * T + min(L, cl)) << 19);
-                                shr_eval<NC>(D, true, d, bc[k], sip, rgM, rgR, s_magic, np, T, cl, Sv[k], Sr[k], Sb[k]);
+                                const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + ((byte & 0x80u) ? 0u : (uint32_t)(NC * 4)) +
+                                                   (uint32_t)((j - n) & (NC - 1)) * 4u;
+                                const uint32_t D = ((uint32_t)n << 2) | (L << 5) | ((F >> 2) << 19);
+                                shr_eval<NC>(D, true, dsh, wbase, lutbase, bc[k], sip, np, T, cl, Sv[k], Sr[k], Sb[k]);
                             }
                         }
-                        uint32_t lm = (rb.y >> 22) & rw[k] & 0x3fu & nmask;   // LEN, every eligible period
+                        uint32_t lm = (rb.y >> 22) & (rw[k] >> 1) & 0x3fu & (nmask >> 1);   // LEN, every eligible period
                         while (lm) {
                             const int n = 32 - __clz(lm);
                             lm &= ~(1u << (n - 1));
@@ -277,10 +306,12 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                             if (!eq) continue;
                             const uint2 cjn = rel[j + n];
                             const int L = (int)(((n <= 4 ? cjn.x : cjn.y) >> ((8 * (n - 1)) & 31)) & 0x7fu);
-                            const int at = ((d - n) & (NP_RING - 1)) * NC + lane * CPL + k;
-                            float base; int run0 = 0;
-                            if ((rw[k] >> (6 + n - 1)) & 1u) base = rgM[at];
-                            else { run0 = (int)(rgR[at] & 0xffffu); base = rgL[at]; if (run0 <= 0) continue; }
+                            const bool start = ((rw[k] >> (6 + n)) & 1u) != 0u;
+                            const uint32_t f = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
+                            const uint32_t ad = (f & (uint32_t)(NC * 128 - 4)) | wbase;
+                            const float base = lds_f(ad);
+                            const int run0 = start ? 0 : (int)(lds_u_off<NC * 4>(ad) & 0xffffu);
+                            if (!start && run0 <= 0) continue;
                             const int call = L + run0 / n + 1;
                             const float cand = base + __ldg(np + ((n - 1) * T + min(L, cl)) * T + min(call, cl));
                             if (cand < Lv[k]) { Lv[k] = cand; Lr[k] = run0 + n; Lb[k] = base; }
@@ -304,9 +335,9 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 Dv[k] = de ? dv2 : dv1;
                 int Dr = de ? (lDM[k] >> 13) + 1 : 1;
                 int run = min(dgr[k] + 1, NP_RUN_SAT);
-                float best = dgv[k] + s_sub[((rw[k] >> 12) & 7u) * 8 + (cc[k].z & 7u)];
+                float best = dgv[k] + lds_f(subbase + ((rw[k] >> 11) & 0xe0u) + (cc[k].z & 0x1cu));
                 if (!steady) {
-                    const int i = Id + r - bc[k], j = jlo + bc[k];
+                    const int i = Id + r - bc[k], j = Dd - r + bc[k];
                     if (ie && i == 1) Ir[k] = 1;
                     if (de && j == 1) Dr = 1;
                     if (i == 0) { Iv[k] = (float)(100 * (j + 1)); Ir[k] = j; }
@@ -338,13 +369,19 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 if (!in[k]) { Sb[k] = Lb[k] = 0.f; Sr[k] = Lr[k] = 0; }
             }
 
-            // ---- history ring + traceback row (slot order)
+            // ---- history ring [ring][array][slot] + traceback row (slot order)
             {
-                const int at = (d & (NP_RING - 1)) * NC + lane * CPL;
+                const uint32_t ad = (((dsh & (uint32_t)(NC * 128 - 1)) + myslot4)) | wbase;
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
-                    rgM[at + k] = Mv[k]; rgS[at + k] = Sb[k]; rgL[at + k] = Lb[k];
-                    rgR[at + k] = (uint32_t)Lr[k] | ((uint32_t)Sr[k] << 16);
+                    if (k == 0) {
+                        sts_f_off<0>(ad, Mv[0]); sts_f_off<NC * 4>(ad, Sb[0]); sts_f_off<NC * 8>(ad, Lb[0]);
+                        sts_u_off<NC * 12>(ad, (uint32_t)Lr[0] | ((uint32_t)Sr[0] << 16));
+                    } else {
+                        const uint32_t adk = ad + (uint32_t)(k * 4);
+                        sts_f_off<0>(adk, Mv[k]); sts_f_off<NC * 4>(adk, Sb[k]); sts_f_off<NC * 8>(adk, Lb[k]);
+                        sts_u_off<NC * 12>(adk, (uint32_t)Lr[k] | ((uint32_t)Sr[k] << 16));
+                    }
                 }
                 uint16_t *rowp = tbp + (size_t)d * (32 * TBS);
                 if (CPL == 2) *reinterpret_cast<uint32_t *>(rowp) = recs[0] | (recs[CPL - 1] << 16);
