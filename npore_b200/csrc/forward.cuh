@@ -74,6 +74,10 @@ template <int OFF> __device__ __forceinline__ void sts_f_off(uint32_t a, float v
 { asm volatile("st.shared.f32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "f"(v) : "memory"); }
 template <int OFF> __device__ __forceinline__ void sts_u_off(uint32_t a, uint32_t v)
 { asm volatile("st.shared.u32 [%0+%1], %2;" :: "r"(a), "n"(OFF), "r"(v) : "memory"); }
+template <int OFF> __device__ __forceinline__ void sts_f2_off(uint32_t a, float v0, float v1)
+{ asm volatile("st.shared.v2.f32 [%0+%1], {%2,%3};" :: "r"(a), "n"(OFF), "f"(v0), "f"(v1) : "memory"); }
+template <int OFF> __device__ __forceinline__ void sts_u2_off(uint32_t a, uint32_t v0, uint32_t v1)
+{ asm volatile("st.shared.v2.u32 [%0+%1], {%2,%3};" :: "r"(a), "n"(OFF), "r"(v0), "r"(v1) : "memory"); }
 
 // History ring of one warp: float ring[NP_RING][4][NC]   (arrays: 0 MAT.VAL, 1 SHR run-start value, 2 LEN run-start
 // value, 3 LEN.RUN | SHR.RUN<<16), NC*128 bytes, aligned to its size so that (offset & mask) | base addresses it.
@@ -82,25 +86,25 @@ template <int NC>
 __device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, uint32_t wbase, uint32_t lutbase, int bc, uint32_t sip,
                                          const float *__restrict__ np, int T, int cl, float &Sv, int &Sr, float &Sb)
 {
-    if (pred) {
-        const uint32_t f = (D >> 17) + dsh;
-        const uint32_t a = (f & (uint32_t)(NC * 128 - 4)) | wbase;
-        const float base = lds_f(a);
-        const uint32_t rr = lds_u_off<NC * 8>(a);                         // array + 2: run word when base is array 1
-        const uint32_t n4 = D & 0x1cu;
-        const uint2 lut = lds_u2(lutbase + n4 * 2u);                      // {ceil(2^31/n), (n-1)*T*T}
-        const bool start = (D & ((uint32_t)NC << 19)) == 0u;              // array bit of the descriptor offset field
-        const int run0 = start ? 0 : (int)(rr >> 16);
-        const bool ok = (bc > (int)((sip >> n4) & 7u)) && (start || run0 > 0);
-        const int q = (int)__umulhi((uint32_t)run0 << 1, lut.x);
-        const int L = (int)((D >> 5) & 0x7fu);
-        const int call = L - q - 1;
-        const uint32_t idx = lut.y + (uint32_t)(min(L, cl) * T) + (uint32_t)min(call, cl);
-        float sc = 100.f;
-        if (call >= 0) sc = __ldg(np + idx);
-        const float cand = base + sc;
-        if (ok && cand < Sv) { Sv = cand; Sr = run0 + (int)(n4 >> 2); Sb = base; }
-    }
+    // straight-line (no branch): a zero descriptor reads valid dummy locations and is rejected by `pred`
+    const uint32_t f = (D >> 17) + dsh;
+    const uint32_t a = (f & (uint32_t)(NC * 128 - 4)) | wbase;
+    const float base = lds_f(a);
+    const uint32_t rr = lds_u_off<NC * 8>(a);                         // array + 2: run word when base is array 1
+    const uint32_t n4 = D & 0x1cu;
+    const uint2 lut = lds_u2(lutbase + n4 * 2u);                      // {ceil(2^31/n), (n-1)*T*T}
+    const bool start = (D & ((uint32_t)NC << 19)) == 0u;              // array bit of the descriptor offset field
+    const int run0 = start ? 0 : (int)(rr >> 16);
+    const bool ok = pred && (bc > (int)((sip >> n4) & 7u)) && (start || run0 > 0);
+    const int q = (int)__umulhi((uint32_t)run0 << 1, lut.x);
+    const int L = (int)((D >> 5) & 0x7fu);
+    const int call = L - q - 1;
+    const uint32_t idx = lut.y + (uint32_t)(min(L, cl) * T) + (uint32_t)max(min(call, cl), 0);
+    float sc = __ldg(np + idx);
+    sc = call >= 0 ? sc : 100.f;
+    const float cand = base + sc;
+    const bool better = ok && cand < Sv;
+    Sv = better ? cand : Sv; Sr = better ? run0 + (int)(n4 >> 2) : Sr; Sb = better ? base : Sb;
 }
 
 template <int CPL>
@@ -372,12 +376,17 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             // ---- history ring [ring][array][slot] + traceback row (slot order)
             {
                 const uint32_t ad = (((dsh & (uint32_t)(NC * 128 - 1)) + myslot4)) | wbase;
+                if (CPL % 2 == 0) {
 #pragma unroll
-                for (int k = 0; k < CPL; k++) {
-                    if (k == 0) {
-                        sts_f_off<0>(ad, Mv[0]); sts_f_off<NC * 4>(ad, Sb[0]); sts_f_off<NC * 8>(ad, Lb[0]);
-                        sts_u_off<NC * 12>(ad, (uint32_t)Lr[0] | ((uint32_t)Sr[0] << 16));
-                    } else {
+                    for (int k = 0; k < CPL; k += 2) {
+                        const uint32_t adk = ad + (uint32_t)(k * 4);
+                        const int k1 = k + 1 < CPL ? k + 1 : k;
+                        sts_f2_off<0>(adk, Mv[k], Mv[k1]); sts_f2_off<NC * 4>(adk, Sb[k], Sb[k1]); sts_f2_off<NC * 8>(adk, Lb[k], Lb[k1]);
+                        sts_u2_off<NC * 12>(adk, (uint32_t)Lr[k] | ((uint32_t)Sr[k] << 16), (uint32_t)Lr[k1] | ((uint32_t)Sr[k1] << 16));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < CPL; k++) {
                         const uint32_t adk = ad + (uint32_t)(k * 4);
                         sts_f_off<0>(adk, Mv[k]); sts_f_off<NC * 4>(adk, Sb[k]); sts_f_off<NC * 8>(adk, Lb[k]);
                         sts_u_off<NC * 12>(adk, (uint32_t)Lr[k] | ((uint32_t)Sr[k] << 16));
