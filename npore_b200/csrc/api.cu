@@ -71,10 +71,11 @@ struct npore_ctx {
     DevBuf d_sub, d_np;
     // batch-resident
     DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
-        d_item_len, d_item_status, d_rle_out, d_rle_len, d_order, d_slots, d_counter, d_ovf, d_ovf_count;
+        d_item_len, d_item_status, d_rleA, d_rleB, d_rle_len, d_rle_which, d_ops_off, d_rle_off, d_pack_ops, d_pack_rle, d_order, d_slots, d_counter, d_ovf, d_ovf_count;
     // per sub-batch scratch
     DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_nf_ref, d_lf_ref, d_nf_seq, d_lf_seq, d_tb;
-    HostBuf h_ops, h_rle, h_small;
+    HostBuf h_small;
+    int64_t pack_ops_total = 0, pack_rle_total = 0;
     std::vector<ItemDesc> items;
     std::vector<int32_t> order;
     std::vector<int32_t> chunk_bmax;
@@ -205,11 +206,11 @@ void npore_ctx_destroy(npore_ctx *ctx)
     cudaSetDevice(ctx->device);
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
-                      &ctx->d_item_status, &ctx->d_rle_out, &ctx->d_rle_len, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
+                      &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
                       &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq,
                       &ctx->d_nf_ref, &ctx->d_lf_ref, &ctx->d_nf_seq, &ctx->d_lf_seq, &ctx->d_tb};
     for (auto *b : bufs) b->release();
-    ctx->h_ops.release(); ctx->h_rle.release(); ctx->h_small.release();
+    ctx->h_small.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->sub_ev) cudaEventDestroy(e);
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -247,7 +248,7 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
     for (int i = 0; i < n; i++) {
         ItemDesc &I = ctx->items[i];
         const int64_t rl = b->ref_len[i], sl = b->seq_len[i];
-        if (rl < 0 || sl < 0 || rl + sl > 0x7ffffff0ll) return fail(ctx, NPORE_ERR_BAD_ARG, "item too long");
+        if (rl < 0 || sl < 0 || rl + sl >= (1ll << 28)) return fail(ctx, NPORE_ERR_BAD_ARG, "item too long (ref_len + seq_len must be < 2^28)");
         if (b->ref_start[i] < 0 || b->ref_start[i] + rl > b->ref_total || b->seq_start[i] < 0 || b->seq_start[i] + sl > b->seq_total)
             return fail(ctx, NPORE_ERR_BAD_ARG, "sequence range outside buffer");
         const int64_t cn = b->cigar_off[i + 1] - b->cigar_off[i];
@@ -304,6 +305,9 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
     CU(ctx->d_item_len.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
     CU(ctx->d_item_status.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
     CU(ctx->d_rle_len.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+    CU(ctx->d_rle_which.ensure(sizeof(int32_t) * (size_t)std::max(n, 1)));
+    CU(ctx->d_ops_off.ensure(sizeof(int64_t) * (size_t)(n + 1)));
+    CU(ctx->d_rle_off.ensure(sizeof(int64_t) * (size_t)(n + 1)));
 
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (n) CU(cudaMemcpyAsync(ctx->d_items.p, ctx->items.data(), sizeof(ItemDesc) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -335,7 +339,14 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     npore_stats &S = ctx->stats;
     S.launches = 0; S.tb_bytes = 0;
     ctx->run_flags = flags;
-    if (flags & NPORE_OUT_RLE) CU(ctx->d_rle_out.ensure(sizeof(uint32_t) * (size_t)(ctx->total_ops + 64)));
+    const bool need_rle = (flags & (NPORE_OUT_RLE | NPORE_OUT_STANDARDIZE)) != 0;
+    const bool want_ops = !(flags & NPORE_OUT_NO_EXPANDED), want_rle = (flags & NPORE_OUT_RLE) != 0;
+    if (need_rle) {
+        CU(ctx->d_rleA.ensure(sizeof(uint32_t) * (size_t)(ctx->total_ops + 64)));
+        CU(ctx->d_rleB.ensure(sizeof(uint32_t) * (size_t)(ctx->total_ops + 64)));
+    }
+    if (want_ops) CU(ctx->d_pack_ops.ensure((size_t)ctx->total_ops + 64));
+    if (want_rle) CU(ctx->d_pack_rle.ensure(sizeof(uint32_t) * (size_t)(ctx->total_ops + 64)));
 
     // ---- sub-batches: greedy over `order` under the scratch budget (sizes from the host-side upper bounds)
     ctx->slots.assign(nchunks, ChunkSlot{});
@@ -427,7 +438,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         ta.tb = fa.tb; ta.ops = ctx->d_scratch_ops.as<uint8_t>(); ta.out = fa.out;
         ta.ovf = fa.ovf; ta.ovf_count = fa.ovf_count; ta.ovf_cap = fa.ovf_cap;
         ta.r = ctx->P.r; ta.W = ctx->P.W; ta.cpl = ctx->cpl; ta.tbs = ctx->tbs;
-        traceback_kernel<<<(sb.count + TB_THREADS - 1) / TB_THREADS, TB_THREADS, 0, ctx->stream>>>(ta);
+        traceback_kernel<<<(sb.count + TB_THREADS / 32 - 1) / (TB_THREADS / 32), TB_THREADS, 0, ctx->stream>>>(ta);
         CU(cudaGetLastError()); S.launches++;
         CU(cudaEventRecord(e3, ctx->stream));
         for (int k = 0; k < sb.count; k++) S.tb_bytes += (int64_t)ctx->chunk_bmax[ctx->order[sb.first + k]] * 64 * ctx->tbs;
@@ -435,23 +446,46 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     // ---- finish
     cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5];
     CU(cudaEventRecord(e0, ctx->stream));
+    const size_t small_bytes = (size_t)n * 12 + (size_t)ctx->n_chunks * sizeof(ChunkOut) + 64;
+    CU(ctx->h_small.ensure(small_bytes));
     if (n) {
         FinishArgs fa{};
         fa.items = ctx->d_items.as<ItemDesc>(); fa.n_items = n; fa.chunk_out = ctx->d_chunk_out.as<ChunkOut>();
         fa.scratch = ctx->d_scratch_ops.as<uint8_t>(); fa.ops = ctx->d_ops.as<uint8_t>();
         fa.item_len = ctx->d_item_len.as<int32_t>(); fa.item_status = ctx->d_item_status.as<int32_t>();
         fa.ref_codes = ctx->d_ref.as<uint8_t>(); fa.seq_codes = ctx->d_seq.as<uint8_t>();
-        fa.rle = ctx->d_rle_out.as<uint32_t>(); fa.rle_len = ctx->d_rle_len.as<int32_t>();
+        fa.rleA = ctx->d_rleA.as<uint32_t>(); fa.rleB = ctx->d_rleB.as<uint32_t>();
+        fa.rle_len = ctx->d_rle_len.as<int32_t>(); fa.rle_which = ctx->d_rle_which.as<int32_t>();
+        fa.to_m = (flags & NPORE_OUT_STANDARDIZE) ? 1 : 0;
+        fa.ops_off = ctx->d_ops_off.as<int64_t>(); fa.rle_off = ctx->d_rle_off.as<int64_t>();
+        fa.pack_ops = ctx->d_pack_ops.as<uint8_t>(); fa.pack_rle = ctx->d_pack_rle.as<uint32_t>();
         gather_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
         CU(cudaGetLastError()); S.launches++;
+        if (need_rle) {
+            rle_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
+            CU(cudaGetLastError()); S.launches++;
+        } else CU(cudaMemsetAsync(ctx->d_rle_len.p, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
         if (flags & NPORE_OUT_STANDARDIZE) {
             standardize_kernel<<<(n + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(fa);
             CU(cudaGetLastError()); S.launches++;
+            if (want_ops) {
+                expand_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
+                CU(cudaGetLastError()); S.launches++;
+            }
         }
-        if (flags & NPORE_OUT_RLE) {
-            rle_kernel<<<(n + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(fa);
+        scan_kernel<<<1, 1024, 0, ctx->stream>>>(fa);
+        CU(cudaGetLastError()); S.launches++;
+        if (want_ops || want_rle) {
+            pack_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa, want_ops ? 1 : 0, want_rle ? 1 : 0);
             CU(cudaGetLastError()); S.launches++;
         }
+        // per-item sizes / status / chunk results travel with the run so that download() knows exact sizes
+        int32_t *h_len = (int32_t *)ctx->h_small.p, *h_status = h_len + n, *h_rlen = h_status + n;
+        ChunkOut *h_co = (ChunkOut *)(h_rlen + n + (n & 1));
+        CU(cudaMemcpyAsync(h_len, ctx->d_item_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h_status, ctx->d_item_status.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(h_rlen, ctx->d_rle_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ctx->n_chunks) CU(cudaMemcpyAsync(h_co, ctx->d_chunk_out.p, sizeof(ChunkOut) * (size_t)ctx->n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -484,61 +518,32 @@ int npore_download(npore_ctx *ctx, npore_result *res)
     const bool want_ops = !(flags & NPORE_OUT_NO_EXPANDED) && res->ops && res->ops_off;
     const bool want_rle = (flags & NPORE_OUT_RLE) && res->rle && res->rle_off;
     npore_stats &S = ctx->stats;
-    S.d2h_bytes = 0;
-    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    // small arrays: item_len, item_status, rle_len, chunk_out
-    const size_t small_bytes = (size_t)n * 12 + (size_t)ctx->n_chunks * sizeof(ChunkOut) + 64;
-    CU(ctx->h_small.ensure(small_bytes));
-    int32_t *h_len = (int32_t *)ctx->h_small.p, *h_status = h_len + n, *h_rlen = h_status + n;
-    ChunkOut *h_co = (ChunkOut *)(h_rlen + n + (n & 1));
-    if (n) {
-        CU(cudaMemcpyAsync(h_len, ctx->d_item_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(h_status, ctx->d_item_status.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (flags & NPORE_OUT_RLE) CU(cudaMemcpyAsync(h_rlen, ctx->d_rle_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        if (ctx->n_chunks) CU(cudaMemcpyAsync(h_co, ctx->d_chunk_out.p, sizeof(ChunkOut) * (size_t)ctx->n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
-        S.d2h_bytes += (int64_t)n * 12 + (int64_t)ctx->n_chunks * sizeof(ChunkOut);
-    }
-    if (want_ops && ctx->total_ops) {
-        CU(ctx->h_ops.ensure((size_t)ctx->total_ops));
-        CU(cudaMemcpyAsync(ctx->h_ops.p, ctx->d_ops.p, (size_t)ctx->total_ops, cudaMemcpyDeviceToHost, ctx->stream));
-        S.d2h_bytes += ctx->total_ops;
-    }
-    if (want_rle && ctx->total_ops) {
-        CU(ctx->h_rle.ensure((size_t)ctx->total_ops * 4));
-        // only the used prefix of each item's region matters, but regions are interleaved: copy all (TODO: device pack)
-        CU(cudaMemcpyAsync(ctx->h_rle.p, ctx->d_rle_out.p, (size_t)ctx->total_ops * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        S.d2h_bytes += ctx->total_ops * 4;
-    }
-    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaEventElapsedTime(&S.ms_d2h, ctx->ev[0], ctx->ev[1]);
-
+    const int32_t *h_len = (const int32_t *)ctx->h_small.p, *h_status = h_len + n, *h_rlen = h_status + n;
+    const ChunkOut *h_co = (const ChunkOut *)(h_rlen + n + (n & 1));
+    // offsets first (sizes arrived with npore_run), then one exact-size copy per output straight into the caller's buffers
     int64_t o = 0, ro = 0, so = 0;
     for (int i = 0; i < n; i++) {
-        const ItemDesc &I = ctx->items[i];
         if (res->status) res->status[i] = h_status[i];
-        if (want_ops) {
-            res->ops_off[i] = o;
-            if (o + h_len[i] > res->ops_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "ops buffer too small");
-            memcpy(res->ops + o, (const uint8_t *)ctx->h_ops.p + I.out_off, (size_t)h_len[i]);
-            o += h_len[i];
-        }
-        if (want_rle) {
-            res->rle_off[i] = ro;
-            if (ro + h_rlen[i] > res->rle_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "rle buffer too small");
-            memcpy(res->rle + ro, (const uint32_t *)ctx->h_rle.p + I.out_off, 4 * (size_t)h_rlen[i]);
-            ro += h_rlen[i];
-        }
+        if (want_ops) { res->ops_off[i] = o; o += h_len[i]; }
+        if (want_rle) { res->rle_off[i] = ro; ro += h_rlen[i]; }
         if (res->chunk_scores && res->score_off) {
+            const ItemDesc &I = ctx->items[i];
             res->score_off[i] = so;
             if (so + I.n_chunks > res->score_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "score buffer too small");
             for (int k = 0; k < I.n_chunks; k++) res->chunk_scores[so + k] = h_co[I.chunk_first + k].score;
             so += I.n_chunks;
         }
     }
-    if (want_ops) res->ops_off[n] = o;
-    if (want_rle) res->rle_off[n] = ro;
+    if (want_ops) { res->ops_off[n] = o; if (o > res->ops_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "ops buffer too small"); }
+    if (want_rle) { res->rle_off[n] = ro; if (ro > res->rle_capacity) return fail(ctx, NPORE_ERR_CAPACITY, "rle buffer too small"); }
     if (res->chunk_scores && res->score_off) res->score_off[n] = so;
+    S.d2h_bytes = (int64_t)n * 12 + (int64_t)ctx->n_chunks * sizeof(ChunkOut);
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (want_ops && o) { CU(cudaMemcpyAsync(res->ops, ctx->d_pack_ops.p, (size_t)o, cudaMemcpyDeviceToHost, ctx->stream)); S.d2h_bytes += o; }
+    if (want_rle && ro) { CU(cudaMemcpyAsync(res->rle, ctx->d_pack_rle.p, 4 * (size_t)ro, cudaMemcpyDeviceToHost, ctx->stream)); S.d2h_bytes += 4 * ro; }
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&S.ms_d2h, ctx->ev[0], ctx->ev[1]);
     return NPORE_OK;
 }
 

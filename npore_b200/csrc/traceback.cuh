@@ -8,7 +8,7 @@
 #pragma once
 #include "common.cuh"
 
-#define TB_THREADS 64
+#define TB_THREADS 128          // 4 warps, one chunk per warp
 
 struct TracebackArgs {
     const ChunkDesc *chunks;
@@ -25,26 +25,29 @@ struct TracebackArgs {
     int r, W, cpl, tbs;
 };
 
+// One warp per chunk: the walk itself is a chain of dependent record loads (every lane reads the same record, a
+// broadcast), but each step emits a whole run, which the 32 lanes write (and, for MAT runs, compare) in parallel.
 __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackArgs a)
 {
-    const int idx = blockIdx.x * TB_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int idx = blockIdx.x * (TB_THREADS / 32) + (threadIdx.x >> 5);
     if (idx >= a.n) return;
     const int cid = a.order[idx];
     const ChunkDesc c = a.chunks[cid];
-    if (!c.valid) { ChunkOut o; o.score = 0.f; o.status = 0; o.start = 0; o.len = 0; a.out[cid] = o; return; }
+    if (!c.valid) { if (lane == 0) { ChunkOut o; o.score = 0.f; o.status = 0; o.start = 0; o.len = 0; a.out[cid] = o; } return; }
     const ChunkSlot sl = a.slots[idx];
     const ItemDesc &I = a.items[c.item];
-    const uint8_t *refs = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
-    const uint8_t *seqs = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
-    const uint16_t *tb = a.tb + (size_t)sl.tb_off * (32 * a.tbs);
+    const uint8_t *__restrict__ refs = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
+    const uint8_t *__restrict__ seqs = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
+    const uint16_t *__restrict__ tb = a.tb + (size_t)sl.tb_off * (32 * a.tbs);
     uint8_t *region = a.ops + I.out_off + c.brk;
-    const int cap = c.B - 1;
+    const int cap = c.B - 1, ncm = 32 * a.cpl - 1;
     int pos = cap, i = c.imax, j = c.jmax, status = 0;
     while (i > 0 || j > 0) {
         if (i < 0) { status = 1; break; }
         if (j < 0) { status = 2; break; }
         // records are stored per anti-diagonal in slot order: slot = column index mod NC (forward.cuh)
-        const int d = i + j, bc = j & (32 * a.cpl - 1);
+        const int d = i + j, bc = j & ncm;
         uint32_t rec = 0;
         if (d < c.B) rec = tb[(size_t)d * (32 * a.tbs) + (bc / a.cpl) * a.tbs + (bc % a.cpl)];
         const int typ = (int)(rec & 7u);
@@ -55,22 +58,25 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
                 if (a.ovf[t].chunk == cid && a.ovf[t].d == d && a.ovf[t].bc == bc) { run = a.ovf[t].run; break; }
         }
         if (run < 1) { status = 3; break; }
-        if (typ == T_INS || typ == T_LEN) {
-            for (int t = 0; t < run && pos > 0; t++) region[--pos] = 'I';
-            i -= run;
-        } else if (typ == T_DEL || typ == T_SHR) {
-            for (int t = 0; t < run && pos > 0; t++) region[--pos] = 'D';
-            j -= run;
+        if (typ == T_INS || typ == T_LEN || typ == T_DEL || typ == T_SHR) {
+            const uint8_t ch = (typ == T_INS || typ == T_LEN) ? 'I' : 'D';
+            const int w = min(run, pos);
+            for (int t = lane; t < w; t += 32) region[pos - 1 - t] = ch;
+            pos -= w;
+            if (ch == 'I') i -= run; else j -= run;
         } else if (typ == T_MAT) {
-            for (int t = 0; t < run; t++) {
-                i--; j--;
-                if (i < 0 || j < 0) break;
-                if (pos > 0) region[--pos] = (refs[j] == seqs[i]) ? '=' : 'X';
-            }
+            const int steps = min(run, min(i, j));                 // cells that exist; a longer run leaves the matrix
+            const int w = min(steps, pos);
+            for (int t = lane; t < w; t += 32) region[pos - 1 - t] = (refs[j - 1 - t] == seqs[i - 1 - t]) ? '=' : 'X';
+            pos -= w;
+            if (steps < run) { i -= steps + 1; j -= steps + 1; } else { i -= run; j -= run; }
         } else { status = 4; break; }
     }
-    ChunkOut o;
-    o.score = a.out[cid].score;
-    o.status = status; o.start = c.brk + pos; o.len = cap - pos;
-    a.out[cid] = o;
+    __syncwarp();
+    if (lane == 0) {
+        ChunkOut o;
+        o.score = a.out[cid].score;
+        o.status = status; o.start = c.brk + pos; o.len = cap - pos;
+        a.out[cid] = o;
+    }
 }
