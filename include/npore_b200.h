@@ -58,6 +58,7 @@ typedef struct npore_ctx npore_ctx;
 #define NPORE_ST_COL_NEG       2
 #define NPORE_ST_RUN_ZERO      3
 #define NPORE_ST_BAD_TYPE      4
+#define NPORE_ST_RUN_OVERFLOW  8    /* an n-polymer (LEN/SHR) run reached the 2047-op record field: CIGAR partial  */
 #define NPORE_ST_BAD_CIGAR     16   /* input CIGAR inconsistent with ref_len / seq_len: item skipped, empty output */
 
 /* output selection flags for npore_run / npore_align_batch */
@@ -105,7 +106,7 @@ typedef struct npore_stats {
     float   ms_h2d, ms_d2h;
     int32_t launches;            /* kernel launches of the last npore_run                                    */
     int32_t n_sub_batches;
-    int32_t overflow_runs;       /* INDEL runs > 8190 routed through the overflow list                        */
+    int32_t overflow_runs;       /* reserved (0)                                                              */
     int32_t sm_count;
 } npore_stats;
 

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnpore_b200.so")
+LIB_PATH = os.environ.get("NPORE_B200_LIB") or os.path.join(HERE, "libnpore_b200.so")   # env override: A/B builds
 
 NPORE_OUT_STANDARDIZE = 1
 NPORE_OUT_RLE = 2

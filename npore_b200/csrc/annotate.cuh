@@ -24,8 +24,8 @@
 //                      .z = [0] generic path (more than two SHR candidates or more than one LEN-eligible period; then
 //                           .x/.y/.w are 0)  [1] k-mer contains N  [2:4] base ref[j-1]  [20:31] 2-bit k-mer ref[j..j+5]
 //                      .w = LEN descriptor of the single LEN-eligible period at j: [2:4] n  [5:11] L  [19:31] ring row offset>>2
-//   rowrec[i] (uint32): [1:6] tract present at i-n (bit n)  [7:12] tract start at i-n (bit 6+n)  [15] k-mer contains N
-//                       [16:18] base seq[i-1]  [20:31] 2-bit k-mer seq[i..i+5]
+//   rowrec[i] (uint32): [4] k-mer contains N  [5:7] base seq[i-1]  [8:13] tract present at i-n (bit 7+n)
+//                       [14:19] tract start at i-n (bit 13+n)  [20:31] 2-bit k-mer seq[i..i+5]   (bits 0-3 are 0)
 #pragma once
 #include "common.cuh"
 
@@ -208,13 +208,13 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
 #pragma unroll
                 for (int n = 1; n <= NP_MAXN; n++) {
                     const uint32_t b = raw_byte(raw, len, i - n, n);
-                    if (b & 0x7fu) v |= 1u << n;
-                    if (b & 0x80u) v |= 1u << (6 + n);
+                    if (b & 0x7fu) v |= 1u << (7 + n);
+                    if (b & 0x80u) v |= 1u << (13 + n);
                 }
                 const uint32_t base = (i >= 1 && i - 1 < len) ? s[i - 1] : 0u;
                 uint32_t hasN = 0;
                 const uint32_t km = kmer2_of(s, len, i, hasN);
-                v |= hasN << 15 | (base & 7u) << 16 | km << 20;
+                v |= hasN << 4 | (base & 7u) << 5 | km << 20;
             }
             out[i] = v;
         }

@@ -119,7 +119,7 @@ inline int chunks_of(int total, int max_b_rows)
 template <int CPL>
 int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 {
-    const size_t smem = (size_t)(FWD_WARPS + 1) * 4 * NP_RING * 32 * CPL * sizeof(float);   // + one ring of alignment slack
+    const size_t smem = (size_t)(FWD_WARPS + FWD_ALIGNED) * 4 * NP_RING * 32 * CPL * sizeof(float);
     CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, FWD_WARPS * 32, smem));

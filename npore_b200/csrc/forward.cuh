@@ -19,7 +19,8 @@
 //     shared-memory ring indexed by physical slot: SHR reads slot s-n (descriptor field), LEN its own slot.  The
 //     ring holds MAT.VAL, both run lengths, and the value at each run's start ("BASE"), which replaces the
 //     lookback of aln.pyx:623-629, 657-663.
-//   * MAT's packed (TYP:3, RUN:13) record -- all that traceback reads (aln.pyx:683-685) -- is streamed to HBM, one
+//   * MAT's packed 16-bit record (TYP, RUN, two INDEL 'extended' bits; common.cuh) -- all that traceback reads
+//     (aln.pyx:683-685) -- is streamed to HBM, one
 //     coalesced 64*CPL-byte row per anti-diagonal, in slot order (traceback indexes it by j mod NC).
 //   * two instantiations of the step: GENERIC (chunk head/tail: first row/column values of aln.pyx:525-528,547-550,
 //     cells outside the chunk, aln.pyx:497-499) and STEADY (every cell 1 <= b_col <= 2r-1 is an interior cell).
@@ -28,7 +29,18 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef FWD_WARPS
 #define FWD_WARPS 4
+#endif
+
+#ifndef FWD_ALIGNED
+#define FWD_ALIGNED 1   // 1: rings aligned to their size (one ring of slack per CTA), cell address = offset | base
+#endif
+#if FWD_ALIGNED
+#define FWD_ADDR(off, base) ((off) | (base))
+#else
+#define FWD_ADDR(off, base) ((off) + (base))
+#endif
 
 struct ForwardArgs {
     const ChunkDesc *chunks;
@@ -80,7 +92,7 @@ template <int OFF> __device__ __forceinline__ void sts_u2_off(uint32_t a, uint32
 { asm volatile("st.shared.v2.u32 [%0+%1], {%2,%3};" :: "r"(a), "n"(OFF), "r"(v0), "r"(v1) : "memory"); }
 
 // History ring of one warp: float ring[NP_RING][4][NC]   (arrays: 0 MAT.VAL, 1 SHR run-start value, 2 LEN run-start
-// value, 3 LEN.RUN | SHR.RUN<<16), NC*128 bytes, aligned to its size so that (offset & mask) | base addresses it.
+// value, 3 LEN.RUN | SHR.RUN<<16), NC*128 bytes; a cell is addressed as (offset & mask) + base.
 // One SHR candidate from a pre-decoded descriptor (aln.pyx:642-667 in gather form; annotate.cuh for the fields).
 template <int NC>
 __device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, uint32_t wbase, uint32_t lutbase, int bc, uint32_t sip,
@@ -88,7 +100,7 @@ __device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, ui
 {
     // straight-line (no branch): a zero descriptor reads valid dummy locations and is rejected by `pred`
     const uint32_t f = (D >> 17) + dsh;
-    const uint32_t a = (f & (uint32_t)(NC * 128 - 4)) | wbase;
+    const uint32_t a = FWD_ADDR(f & (uint32_t)(NC * 128 - 4), wbase);
     const float base = lds_f(a);
     const uint32_t rr = lds_u_off<NC * 8>(a);                         // array + 2: run word when base is array 1
     const uint32_t n4 = D & 0x1cu;
@@ -104,11 +116,23 @@ __device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, ui
     sc = call >= 0 ? sc : 100.f;
     const float cand = base + sc;
     const bool better = ok && cand < Sv;
-    Sv = better ? cand : Sv; Sr = better ? run0 + (int)(n4 >> 2) : Sr; Sb = better ? base : Sb;
+    Sv = better ? cand : Sv; Sr = better ? min(run0 + (int)(n4 >> 2), NP_RUN_SAT) : Sr; Sb = better ? base : Sb;
 }
 
+#ifndef FWD_MINB
+#define FWD_MINB 1      // >1: min resident CTAs hint (measured: the hint makes ptxas schedule worse at equal registers)
+#endif
+#ifndef FWD_MAXREG
+#define FWD_MAXREG 0
+#endif
 template <int CPL>
+#if FWD_MAXREG
+__global__ void __launch_bounds__(FWD_WARPS * 32) __maxnreg__(CPL <= 2 ? FWD_MAXREG : 255) forward_kernel(const ForwardArgs a)
+#elif FWD_MINB > 1
+__global__ void __launch_bounds__(FWD_WARPS * 32, (CPL <= 2 ? FWD_MINB : CPL <= 4 ? 12 : 8) / FWD_WARPS) forward_kernel(const ForwardArgs a)
+#else
 __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardArgs a)
+#endif
 {
     constexpr int NC = 32 * CPL;
     constexpr int TBS = CPL <= 1 ? 1 : CPL <= 2 ? 2 : CPL <= 4 ? 4 : 8;
@@ -117,16 +141,20 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
     __shared__ float s_sub[64];
     __shared__ uint2 s_lut[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 64) {
-        const int sb = threadIdx.x >> 3, rb = threadIdx.x & 7;
-        s_sub[threadIdx.x] = (sb < 5 && rb < 5) ? a.sub_tab[sb * 5 + rb] : 0.f;
+    for (int t = threadIdx.x; t < 64; t += FWD_WARPS * 32) {
+        const int sb = t >> 3, rb = t & 7;
+        s_sub[t] = (sb < 5 && rb < 5) ? a.sub_tab[sb * 5 + rb] : 0.f;
     }
     if (threadIdx.x < 8) {
         const uint32_t n = threadIdx.x;
         s_lut[n] = make_uint2(n >= 1 ? (uint32_t)((0x80000000ull + n - 1) / n) : 0u, n >= 1 ? (n - 1) * a.P.np_dim * a.P.np_dim : 0u);
     }
     __syncthreads();
+#if FWD_ALIGNED
     const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem) + RING_BYTES - 1u) & ~(RING_BYTES - 1u);
+#else
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
+#endif
     const uint32_t wbase = smem_base + (uint32_t)warp * RING_BYTES;
     const uint32_t subbase = (uint32_t)__cvta_generic_to_shared(s_sub);
     const uint32_t lutbase = (uint32_t)__cvta_generic_to_shared(s_lut);
@@ -134,7 +162,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
 
     const int r = a.P.r, T = a.P.np_dim, cl = a.P.np_clamp;
     const float gopen = a.P.gap_open, gext = a.P.gap_ext;
-    const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 1;       // rowrec "present" bits live at [1:6]
+    const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 8;       // rowrec "present" bits live at [8:13]
     const float *__restrict__ np = a.np_tab;
     const int src_lane = (lane + 31) & 31;
 
@@ -159,11 +187,11 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
 
         // ---- per-slot state.  At d = 0: jlo = -r, slot s holds column j = -r + ((s + r) mod NC), row i = -j.
         float Mv1[CPL], Iv1[CPL], Dv1[CPL], dgv[CPL];   // previous anti-diagonal: MAT/INS/DEL values; diag MAT value
-        int Ir1[CPL], DM1[CPL], dgr[CPL];                 // INS.RUN; DEL.RUN<<13 | matrun; diag matrun
+        int Mr1[CPL], dgr[CPL];                           // matrun (RUN if TYP==MAT else 0) of the cell; of the diag cell
         uint4 cc[CPL]; uint32_t rw[CPL]; int bc[CPL];
 #pragma unroll
         for (int k = 0; k < CPL; k++) {
-            Mv1[k] = Iv1[k] = Dv1[k] = dgv[k] = 0.f; Ir1[k] = DM1[k] = dgr[k] = 0;
+            Mv1[k] = Iv1[k] = Dv1[k] = dgv[k] = 0.f; Mr1[k] = dgr[k] = 0;
             const int s = lane * CPL + k;
             bc[k] = (s + r) & (NC - 1);
             const int j0 = bc[k] - r;
@@ -180,7 +208,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
         const int idLo = r + 1, idSpan = imax - 2 * r, ddSpan = jmax - 2 * r;
 
         for (int d = 0; d < B; d++) {
-            float lMv[CPL], lDv[CPL]; int lDM[CPL];
+            float lMv[CPL], lDv[CPL]; int lMr[CPL];
             if (d > 0) {
                 const int g = c.brk + d - 1;                 // op that leads to this anti-diagonal
                 if ((g & 31) == 0 && d > 1) {
@@ -193,13 +221,13 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 infd += 100.f;
                 const float a0 = __shfl_sync(NP_FULL, Mv1[CPL - 1], src_lane);
                 const float a1 = __shfl_sync(NP_FULL, Dv1[CPL - 1], src_lane);
-                const int a2 = __shfl_sync(NP_FULL, DM1[CPL - 1], src_lane);
+                const int a2 = __shfl_sync(NP_FULL, Mr1[CPL - 1], src_lane);
                 const uint32_t a3 = __shfl_sync(NP_FULL, rw[CPL - 1], src_lane);
 #pragma unroll
                 for (int k = CPL - 1; k >= 0; k--) {
                     lMv[k] = k ? Mv1[k > 0 ? k - 1 : 0] : a0;
                     lDv[k] = k ? Dv1[k > 0 ? k - 1 : 0] : a1;
-                    lDM[k] = k ? DM1[k > 0 ? k - 1 : 0] : a2;
+                    lMr[k] = k ? Mr1[k > 0 ? k - 1 : 0] : a2;
                     rw[k] = k ? rw[k > 0 ? k - 1 : 0] : a3;
                 }
                 if (o) {
@@ -217,7 +245,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < CPL; k++) { lMv[k] = lDv[k] = 0.f; lDM[k] = 0; }
+                for (int k = 0; k < CPL; k++) { lMv[k] = lDv[k] = 0.f; lMr[k] = 0; }
             }
             const uint32_t sip = c_sipack[hist];
             const float edgev = infd + 100.f;
@@ -241,7 +269,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 p0[k] = in[k] && cc[k].x != 0u;
                 p1[k] = in[k] && cc[k].y != 0u;
                 pg[k] = in[k] && (cc[k].z & 1u);
-                pl[k] = in[k] && (((rw[k] & nmask) >> ((cc[k].w >> 2) & 7u)) & 1u);   // rowrec bit 0 is always 0
+                pl[k] = in[k] && (((rw[k] & nmask) >> (((cc[k].w >> 2) & 7u) + 7u)) & 1u);   // rowrec bit 7 is always 0
                 any1 |= p1[k]; anyg |= pg[k]; anyl |= pl[k];
             }
             // ---- SHR gather: descriptor 0 (largest period; some lane almost always has one), then descriptor 1
@@ -257,15 +285,15 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 for (int k = 0; k < CPL; k++) {
                     if (pl[k]) {
                         const uint32_t D = cc[k].w;
-                        if ((cc[k].z | (rw[k] >> 14)) & 2u) {
+                        if ((cc[k].z | (rw[k] >> 3)) & 2u) {
                             pg[k] = true; anyg = true;             // an N inside a k-mer: byte-wise compare on the generic path
                         } else {
                             const uint32_t n4 = D & 0x1cu;
                             const int n = (int)(n4 >> 2);
                             const bool eq = (((cc[k].z ^ rw[k]) >> 20) << (32 - 2 * n)) == 0u;
-                            const bool start = ((rw[k] >> (6 + n)) & 1u) != 0u;
+                            const bool start = ((rw[k] >> (13 + n)) & 1u) != 0u;
                             const uint32_t f = (D >> 17) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
-                            const uint32_t ad = (f & (uint32_t)(NC * 128 - 4)) | wbase;
+                            const uint32_t ad = FWD_ADDR(f & (uint32_t)(NC * 128 - 4), wbase);
                             const float base = lds_f(ad);
                             const uint32_t rr = lds_u_off<NC * 4>(ad);                 // array 2 + 1 = run word
                             const uint2 lut = lds_u2(lutbase + n4 * 2u);
@@ -275,7 +303,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                             const int L = (int)((D >> 5) & 0x7fu);
                             const int call = L + q + 1;
                             const float cand = base + __ldg(np + (lut.y + (uint32_t)(min(L, cl) * T) + (uint32_t)min(call, cl)));
-                            if (ok && cand < Lv[k]) { Lv[k] = cand; Lr[k] = run0 + n; Lb[k] = base; }
+                            if (ok && cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + n, NP_RUN_SAT); Lb[k] = base; }
                         }
                     }
                 }
@@ -298,7 +326,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                                 shr_eval<NC>(D, true, dsh, wbase, lutbase, bc[k], sip, np, T, cl, Sv[k], Sr[k], Sb[k]);
                             }
                         }
-                        uint32_t lm = (rb.y >> 22) & (rw[k] >> 1) & 0x3fu & (nmask >> 1);   // LEN, every eligible period
+                        uint32_t lm = (rb.y >> 22) & ((rw[k] & nmask) >> 8) & 0x3fu;   // LEN, every eligible period
                         while (lm) {
                             const int n = 32 - __clz(lm);
                             lm &= ~(1u << (n - 1));
@@ -310,15 +338,15 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                             if (!eq) continue;
                             const uint2 cjn = rel[j + n];
                             const int L = (int)(((n <= 4 ? cjn.x : cjn.y) >> ((8 * (n - 1)) & 31)) & 0x7fu);
-                            const bool start = ((rw[k] >> (6 + n)) & 1u) != 0u;
+                            const bool start = ((rw[k] >> (13 + n)) & 1u) != 0u;
                             const uint32_t f = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
-                            const uint32_t ad = (f & (uint32_t)(NC * 128 - 4)) | wbase;
+                            const uint32_t ad = FWD_ADDR(f & (uint32_t)(NC * 128 - 4), wbase);
                             const float base = lds_f(ad);
                             const int run0 = start ? 0 : (int)(lds_u_off<NC * 4>(ad) & 0xffffu);
                             if (!start && run0 <= 0) continue;
                             const int call = L + run0 / n + 1;
                             const float cand = base + __ldg(np + ((n - 1) * T + min(L, cl)) * T + min(call, cl));
-                            if (cand < Lv[k]) { Lv[k] = cand; Lr[k] = run0 + n; Lb[k] = base; }
+                            if (cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + n, NP_RUN_SAT); Lb[k] = base; }
                         }
                     }
                 }
@@ -326,56 +354,42 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
 
             // ---- INS / DEL / MAT (aln.pyx:525-592)
             uint32_t recs[CPL];
-            float Mv[CPL], Iv[CPL], Dv[CPL]; int Ir[CPL], DM[CPL];
+            float Mv[CPL], Iv[CPL], Dv[CPL]; int Mr[CPL];
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
-                // INS from top = own previous value; DEL from left
+                // INS from top = own previous value; DEL from left.  Only the "extended" bits are kept (see common.cuh)
                 const float iv1 = Mv1[k] + gopen, iv2 = Iv1[k] + gext;
-                const bool ie = iv2 < iv1;
+                bool ie = iv2 < iv1;
                 Iv[k] = ie ? iv2 : iv1;
-                Ir[k] = ie ? Ir1[k] + 1 : 1;
                 const float dv1 = lMv[k] + gopen, dv2 = lDv[k] + gext;
-                const bool de = dv2 < dv1;
+                bool de = dv2 < dv1;
                 Dv[k] = de ? dv2 : dv1;
-                int Dr = de ? (lDM[k] >> 13) + 1 : 1;
-                int run = min(dgr[k] + 1, NP_RUN_SAT);
-                float best = dgv[k] + lds_f(subbase + ((rw[k] >> 11) & 0xe0u) + (cc[k].z & 0x1cu));
+                uint32_t pk = (uint32_t)min(dgr[k] + 1, NP_RUN_SAT);                 // typ MAT = 0
+                float best = dgv[k] + lds_f(subbase + (rw[k] & 0xe0u) + (cc[k].z & 0x1cu));
                 if (!steady) {
                     const int i = Id + r - bc[k], j = Dd - r + bc[k];
-                    if (ie && i == 1) Ir[k] = 1;
-                    if (de && j == 1) Dr = 1;
-                    if (i == 0) { Iv[k] = (float)(100 * (j + 1)); Ir[k] = j; }
-                    if (j == 0) { Dv[k] = (float)(100 * (i + 1)); Dr = i; }
-                    if (!(i > 0 && j > 0)) { best = Dv[k] + 100.f; run = 0; }
+                    if (i <= 1) ie = false;                                          // aln.pyx:537-538 (run restarts), :525-528
+                    if (j <= 1) de = false;                                          // aln.pyx:559-560, :547-550
+                    if (i == 0) Iv[k] = (float)(100 * (j + 1));
+                    if (j == 0) Dv[k] = (float)(100 * (i + 1));
+                    if (!(i > 0 && j > 0)) { best = Dv[k] + 100.f; pk = 0u; }
                 }
-                uint32_t pk = (uint32_t)run << 3;                                  // typ MAT = 0
-                if (Iv[k] < best) { best = Iv[k]; pk = ((uint32_t)Ir[k] << 3) | T_INS; }
-                if (Lv[k] < best) { best = Lv[k]; pk = ((uint32_t)Lr[k] << 3) | T_LEN; }
-                if (Dv[k] < best) { best = Dv[k]; pk = ((uint32_t)Dr << 3) | T_DEL; }
-                if (Sv[k] < best) { best = Sv[k]; pk = ((uint32_t)Sr[k] << 3) | T_SHR; }
-                if (pk >= (((uint32_t)NP_RUN_SAT << 3) | 1u) && in[k]) {          // non-MAT run beyond the 13-bit field
-                    if ((pk & 7u) != 0u) {
-                        const int pos = atomicAdd(a.ovf_count, 1);
-                        if (pos < a.ovf_cap) { OverflowRec ov; ov.chunk = cid; ov.d = d; ov.bc = lane * CPL + k; ov.run = (int)(pk >> 3); a.ovf[pos] = ov; }
-                        pk = ((uint32_t)NP_RUN_SAT << 3) | (pk & 7u);
-                    }
-                }
+                if (Iv[k] < best) { best = Iv[k]; pk = (uint32_t)T_INS << NP_REC_TYP; }
+                if (Lv[k] < best) { best = Lv[k]; pk = ((uint32_t)T_LEN << NP_REC_TYP) + (uint32_t)Lr[k]; }
+                if (Dv[k] < best) { best = Dv[k]; pk = (uint32_t)T_DEL << NP_REC_TYP; }
+                if (Sv[k] < best) { best = Sv[k]; pk = ((uint32_t)T_SHR << NP_REC_TYP) + (uint32_t)Sr[k]; }
                 // EDGE (b_col 0 / 2r): every state INF*(b_row+1), TYP MAT, RUN 0 (aln.pyx:502-507).  Cells outside the chunk
                 // (aln.pyx:497-499) are never read by interior cells; they get the same harmless value.
                 Mv[k] = in[k] ? best : edgev;
                 Iv[k] = in[k] ? Iv[k] : edgev;
                 Dv[k] = in[k] ? Dv[k] : edgev;
-                Ir[k] = in[k] ? Ir[k] : 0;
-                pk = in[k] ? pk : 0u;
-                recs[k] = pk;
-                const int mr = (pk & 7u) ? 0 : (int)(pk >> 3);
-                DM[k] = ((in[k] ? Dr : 0) << 13) | mr;
-                if (!in[k]) { Sb[k] = Lb[k] = 0.f; Sr[k] = Lr[k] = 0; }
+                Mr[k] = (in[k] && pk < (1u << NP_REC_TYP)) ? (int)pk : 0;
+                recs[k] = in[k] ? (pk | (ie ? NP_REC_IE : 0u) | (de ? NP_REC_DE : 0u)) : 0u;
             }
 
             // ---- history ring [ring][array][slot] + traceback row (slot order)
             {
-                const uint32_t ad = (((dsh & (uint32_t)(NC * 128 - 1)) + myslot4)) | wbase;
+                const uint32_t ad = FWD_ADDR((dsh & (uint32_t)(NC * 128 - 1)) + myslot4, wbase);
                 if (CPL % 2 == 0) {
 #pragma unroll
                     for (int k = 0; k < CPL; k += 2) {
@@ -402,8 +416,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
-                dgv[k] = lMv[k]; dgr[k] = lDM[k] & 8191;          // next step's diagonal neighbour = this step's left
-                Mv1[k] = Mv[k]; Iv1[k] = Iv[k]; Dv1[k] = Dv[k]; Ir1[k] = Ir[k]; DM1[k] = DM[k];
+                dgv[k] = lMv[k]; dgr[k] = lMr[k];                 // next step's diagonal neighbour = this step's left
+                Mv1[k] = Mv[k]; Iv1[k] = Iv[k]; Dv1[k] = Dv[k]; Mr1[k] = Mr[k];
             }
         }
         // chunk score = MAT value of the end cell (b_col == r on the last anti-diagonal)

@@ -43,20 +43,25 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
     uint8_t *region = a.ops + I.out_off + c.brk;
     const int cap = c.B - 1, ncm = 32 * a.cpl - 1;
     int pos = cap, i = c.imax, j = c.jmax, status = 0;
+    const size_t rs = (size_t)32 * a.tbs;
+#define TB_REC(dd, jj) ((dd) >= 0 && (dd) < c.B ? (uint32_t)tb[(size_t)(dd) * rs + (((jj) & ncm) / a.cpl) * a.tbs + (((jj) & ncm) % a.cpl)] : 0u)
     while (i > 0 || j > 0) {
         if (i < 0) { status = 1; break; }
         if (j < 0) { status = 2; break; }
         // records are stored per anti-diagonal in slot order: slot = column index mod NC (forward.cuh)
-        const int d = i + j, bc = j & ncm;
-        uint32_t rec = 0;
-        if (d < c.B) rec = tb[(size_t)d * (32 * a.tbs) + (bc / a.cpl) * a.tbs + (bc % a.cpl)];
-        const int typ = (int)(rec & 7u);
-        int run = (int)(rec >> 3);
-        if (typ != T_MAT && run == NP_RUN_SAT) {
-            const int m = min(*a.ovf_count, a.ovf_cap);
-            for (int t = 0; t < m; t++)
-                if (a.ovf[t].chunk == cid && a.ovf[t].d == d && a.ovf[t].bc == bc) { run = a.ovf[t].run; break; }
-        }
+        const int d = i + j;
+        const uint32_t rec = TB_REC(d, j);
+        const int typ = (int)(rec >> NP_REC_TYP);
+        int run = (int)(rec & (uint32_t)NP_RUN_SAT);
+        if (typ == T_INS) {             // RUN = number of consecutive extensions up the column + 1 (aln.pyx:537-543)
+            run = 1;
+            uint32_t q = rec; int ii = i;
+            while ((q & NP_REC_IE) && ii > 0) { run++; ii--; q = TB_REC(ii + j, j); }
+        } else if (typ == T_DEL) {      // likewise along the row (aln.pyx:559-565)
+            run = 1;
+            uint32_t q = rec; int jj = j;
+            while ((q & NP_REC_DE) && jj > 0) { run++; jj--; q = TB_REC(i + jj, jj); }
+        } else if ((typ == T_LEN || typ == T_SHR) && run == NP_RUN_SAT) { status = 8; break; }   // run field overflow
         if (run < 1) { status = 3; break; }
         if (typ == T_INS || typ == T_LEN || typ == T_DEL || typ == T_SHR) {
             const uint8_t ch = (typ == T_INS || typ == T_LEN) ? 'I' : 'D';
@@ -72,6 +77,7 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
             if (steps < run) { i -= steps + 1; j -= steps + 1; } else { i -= run; j -= run; }
         } else { status = 4; break; }
     }
+#undef TB_REC
     __syncwarp();
     if (lane == 0) {
         ChunkOut o;
