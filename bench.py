@@ -204,7 +204,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import ref_loader
         kind = "reference" if ref_loader.available() else "port"
-        per_step = max(16, min(len(reads), 2 * cores)) if kind == "reference" else 8
+        per_step = max(32, min(len(reads), 8 * cores)) if kind == "reference" else 8
         times = []
         for s in range(args.warmup + args.steps):
             sample = reads[(s * per_step) % max(1, len(reads) - per_step):][:per_step]

@@ -237,3 +237,58 @@ def test_full_c2_properties(tables):
         want, wsc, _ = oracle.align(oracle.bases_to_int(rd[9]), oracle.bases_to_int(rd[7]), cig.expand_cigar(rd[5]), S, NP, return_scores=True)
         assert res.ops_str(k) == want and np.array_equal(res.scores(k), wsc)
     eng.close()
+
+
+@pytest.mark.parametrize("r", [10, 30, 60, 100])
+def test_c4_long_reads_band_and_window_sweep(tables, engine_factory, r):
+    """BASELINE.json configs[3]: 50-100 kb reads, band radius x max_b_rows sweep (many chunks per read)."""
+    S, NP = tables
+    rng = np.random.default_rng(400 + r)
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(160_000, rng)
+    reads = synth.make_reads(ref, 1, 55_000, rng, cm, tracts=tr) + synth.make_reads(ref, 1, 90_000, rng, cm, tracts=tr)
+    cases = [(rd[9], rd[7], cig.expand_cigar(rd[5])) for rd in reads]
+    for mb in (5000, 20000, 50000):
+        want = _oracle_all(cases, S, NP, max_b_rows=mb, r=r)
+        assert len(want[1][1]) == -(-(len(cases[1][0]) + len(cases[1][1])) // (mb - 1))      # chunk count (aln.pyx:344-358)
+        _check(engine_factory(max_b_rows=mb, r=r), cases, want)
+
+
+def test_c5_whole_contig_haplotypes(tables, golden):
+    """BASELINE.json configs[4]: haplotypes carrying indels inside n-polymer tracts, one align() item per
+    haplotype of a whole contig (dozens of chunks), through bam.realign_haps (bam.pyx:93-123)."""
+    from npore_b200 import bam, cfg
+    S, NP = tables
+    cfg.args.sub_scores, cfg.args.np_scores = S, NP
+    cfg.args.max_n, cfg.args.max_l = 6, 100
+    rng = np.random.default_rng(55)
+    cm = synth.call_length_model(NP)
+    haps = []
+    for ctg, length in (("chrA", 300_000), ("chrB", 120_000)):
+        ref, tr = synth.make_reference_with_tracts(length, rng)
+        for hap in (1, 2):
+            keep = tr[rng.random(len(tr)) < 0.5]                      # variants = unit-multiple indels at tract ends only
+            seq, cg = synth.make_read(ref, rng, cm, p_ins=0.0, p_sub=0.0005, p_del=0.0, tracts=keep)
+            haps.append((ctg, hap, seq, ref, cg))
+    got = bam.realign_haps(haps)
+    for h, g in zip(haps, got):
+        ir, iq = oracle.bases_to_int(h[3]), oracle.bases_to_int(h[2])
+        want = oracle.standardize(oracle.align(ir, iq, h[4], S, NP), ir, iq)
+        assert g[:4] == h[:4] and g[4] == want
+
+
+def test_realign_reads_streams_in_batches(tables, tmp_path):
+    """The batch scheduler cuts a lazy read stream into several GPU batches; records stay in input order."""
+    from npore_b200 import bam, cfg
+    S, NP = tables
+    cfg.args.sub_scores, cfg.args.np_scores = S, NP
+    cfg.args.out_prefix = str(tmp_path / "o")
+    rng = np.random.default_rng(8)
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(40_000, rng)
+    reads = synth.make_reads(ref, 40, 2000, rng, cm, tracts=tr)
+    lines = bam.realign_reads(iter(reads), max_batch_ops=30_000)               # ~7 reads per batch
+    assert [l.split("\t")[0] for l in lines] == [r[0] for r in reads]
+    for rd, line in zip(reads, lines):
+        assert line.split("\t")[5] == oracle.realign_cigar(rd[9], rd[7], rd[5], S, NP)
+    assert cfg.counter.value >= 40
