@@ -5,8 +5,7 @@
 // The reference scans positions sequentially with "don't overwrite" rules (aln.pyx:238-249).  Equivalent
 // parallel form, for n = 1..max_n in order (the `longest` test of period n reads final L of periods < n):
 //   e[q]   = (q+n < len && s[q]==s[q+n])
-//   runs   = maximal stretches of e==true plus their terminating false position; nf[q] / lf[q] = next / last
-//            false position (two tile scans)
+//   runs   = maximal stretches of e==true plus their terminating false position
 //   chains = positions of one run congruent mod n.  One walker per chain head visits its chain in ascending
 //            order carrying (first active writer, last active writer with l > max_l) -- that is all the
 //            sequential overwrite rules can depend on (incl. the max_l clamp quirk).
@@ -39,64 +38,33 @@ struct AnnotateArgs {
     const ItemDesc *items;
     const uint8_t *ref_codes, *seq_codes;
     uint8_t *raw_ref, *raw_seq;    // 8 B per entry
-    int32_t *nf_ref, *lf_ref, *nf_seq, *lf_seq;
     uint4 *colrec; uint2 *relaid; uint32_t *rowrec;
     int max_n, max_l, nc, np_dim, np_clamp;
 };
 
 // np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
-__device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n, int max_l,
-                               uint8_t *raw, int32_t *nf, int32_t *lf, int32_t *full_out)
+// Per period n every position decides locally whether it heads a phase chain (fewer than n equalities e[] immediately
+// before it), finds the end of its run by walking forward, and walks its chain; chains of one period write disjoint
+// bytes, so one barrier per period suffices (the `longest` test reads the bytes of smaller periods).
+__device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n, int max_l, uint8_t *raw, int32_t *full_out)
 {
-    __shared__ int s_ff[ANN_THREADS], s_lfp[ANN_THREADS];
     const int tid = threadIdx.x;
     for (int q = tid; q < len; q += ANN_THREADS) reinterpret_cast<uint2 *>(raw)[q] = make_uint2(0u, 0u);
     if (full_out) for (int q = tid; q < len * 2 * max_n; q += ANN_THREADS) full_out[q] = 0;
-    const int T = (len + ANN_THREADS - 1) / ANN_THREADS;
-    const int t0 = min(len, tid * T), t1 = min(len, t0 + T);
     __syncthreads();
-
     for (int n = 1; n <= max_n; n++) {
-        // ---- tile summaries: first / last false position of e[] in my tile
-        int ff = 0x7fffffff, lfp = -1;
-        for (int q = t0; q < t1; q++) {
-            const bool e = (q + n < len) && (s[q] == s[q + n]);
-            if (!e) { if (ff == 0x7fffffff) ff = q; lfp = q; }
-        }
-        s_ff[tid] = ff; s_lfp[tid] = lfp;
-        __syncthreads();
-        // suffix-min of ff over later tiles, prefix-max of lfp over earlier tiles (Hillis-Steele)
-        for (int o = 1; o < ANN_THREADS; o <<= 1) {
-            int a = s_ff[tid], b = s_lfp[tid];
-            if (tid + o < ANN_THREADS) a = min(a, s_ff[tid + o]);
-            if (tid >= o) b = max(b, s_lfp[tid - o]);
-            __syncthreads();
-            s_ff[tid] = a; s_lfp[tid] = b;
-            __syncthreads();
-        }
-        int nxt = (tid + 1 < ANN_THREADS) ? s_ff[tid + 1] : 0x7fffffff;   // first false after my tile
-        int prv = tid ? s_lfp[tid - 1] : -1;                              // last false before my tile
-        if (nxt == 0x7fffffff) nxt = len;
-        for (int q = t1 - 1; q >= t0; q--) {
-            const bool e = (q + n < len) && (s[q] == s[q + n]);
-            if (!e) nxt = q;
-            nf[q] = nxt;
-        }
-        for (int q = t0; q < t1; q++) {
-            lf[q] = prv;
-            const bool e = (q + n < len) && (s[q] == s[q + n]);
-            if (!e) prv = q;
-        }
-        __syncthreads();
-        // ---- one walker per chain head
         for (int h = tid; h < len; h += ANN_THREADS) {
-            const int rs = lf[h] + 1;
-            if (h - rs >= n) continue;
-            const int end = nf[rs];
+            int t = 0;                                        // equalities immediately before h
+            while (t < n && h - t - 1 >= 0 && h - t - 1 + n < len && s[h - t - 1] == s[h - t - 1 + n]) t++;
+            if (t == n) continue;                             // not among the first n positions of its run
+            int end = h;                                      // first position >= h with e[] false
+            while (end + n < len && s[end] == s[end + n]) end++;
+            if (end - h < 2 * n) continue;                    // fewer than 3 copies from the chain head on: nothing to write
             int first = -1, lfirst = 0, zlast = -1;
             for (int p = h; p <= end; p += n) {
                 const int m = end - p;
                 int l = m / n; if (l > 0) l++;
+                if (l <= 2 && first < 0) break;               // l only decreases along the chain
                 bool act = s[p] != 0 && l > 2;
                 if (act) {
                     const uint2 rw = reinterpret_cast<const uint2 *>(raw)[p];
@@ -155,7 +123,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         const int len = c.rlen;
         const uint8_t *s = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
         uint8_t *raw = a.raw_ref + sl.col_off * 8;
-        annotate_slice(s, len, a.max_n, a.max_l, raw, a.nf_ref + sl.col_off, a.lf_ref + sl.col_off, nullptr);
+        annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr);
         uint4 *out = a.colrec + sl.col_off;
         uint2 *rel = a.relaid + sl.col_off;
         const int NC = a.nc;
@@ -200,7 +168,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         const int len = c.slen;
         const uint8_t *s = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
         uint8_t *raw = a.raw_seq + sl.row_off * 8;
-        annotate_slice(s, len, a.max_n, a.max_l, raw, a.nf_seq + sl.row_off, a.lf_seq + sl.row_off, nullptr);
+        annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr);
         uint32_t *out = a.rowrec + sl.row_off;
         for (int i = threadIdx.x; i < sl.row_cap; i += ANN_THREADS) {
             uint32_t v = 0;
@@ -223,7 +191,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
 
 // src/aln.pyx:179-251 as a stand-alone device entry (npore_get_np_info): one CTA, one sequence.
 __global__ void __launch_bounds__(ANN_THREADS)
-np_info_kernel(const uint8_t *s, int len, int max_n, int max_l, uint8_t *raw, int32_t *nf, int32_t *lf, int32_t *out)
+np_info_kernel(const uint8_t *s, int len, int max_n, int max_l, uint8_t *raw, int32_t *out)
 {
-    annotate_slice(s, len, max_n, max_l, raw, nf, lf, out);
+    annotate_slice(s, len, max_n, max_l, raw, out);
 }

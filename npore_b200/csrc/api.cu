@@ -73,7 +73,7 @@ struct npore_ctx {
     DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
         d_item_len, d_item_status, d_rleA, d_rleB, d_rle_len, d_rle_which, d_ops_off, d_rle_off, d_pack_ops, d_pack_rle, d_order, d_slots, d_counter, d_ovf, d_ovf_count;
     // per sub-batch scratch
-    DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_nf_ref, d_lf_ref, d_nf_seq, d_lf_seq, d_tb;
+    DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_tb;
     HostBuf h_small;
     int64_t pack_ops_total = 0, pack_rle_total = 0;
     std::vector<ItemDesc> items;
@@ -207,8 +207,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
                       &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
-                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq,
-                      &ctx->d_nf_ref, &ctx->d_lf_ref, &ctx->d_nf_seq, &ctx->d_lf_seq, &ctx->d_tb};
+                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb};
     for (auto *b : bufs) b->release();
     ctx->h_small.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -353,7 +352,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     ctx->subs.clear();
     size_t max_col = 0, max_row = 0, max_tb = 0;
     {
-        const size_t per_entry = 16 + 8 + 8 + 4 + 4 + 4 + 8 + 4 + 4;   // colrec, relaid, raw_ref, nf/lf ref, rowrec, raw_seq, nf/lf seq
+        const size_t per_entry = 16 + 8 + 8 + 4 + 8;   // colrec, relaid, raw_ref, rowrec, raw_seq
         size_t col = 0, row = 0, tb = 0; int first = 0;
         for (int64_t k = 0; k < nchunks; k++) {
             const int bm = ctx->chunk_bmax[ctx->order[k]];
@@ -375,9 +374,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         }
     }
     CU(ctx->d_colrec.ensure(max_col * 16 + 64)); CU(ctx->d_relaid.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
-    CU(ctx->d_nf_ref.ensure(max_col * 4 + 64)); CU(ctx->d_lf_ref.ensure(max_col * 4 + 64));
     CU(ctx->d_rowrec.ensure(max_row * 4 + 64)); CU(ctx->d_raw_seq.ensure(max_row * 8 + 64));
-    CU(ctx->d_nf_seq.ensure(max_row * 4 + 64)); CU(ctx->d_lf_seq.ensure(max_row * 4 + 64));
     CU(ctx->d_tb.ensure(max_tb * (size_t)(64 * ctx->tbs) + 256));
     if (nchunks) CU(cudaMemcpyAsync(ctx->d_slots.p, ctx->slots.data(), sizeof(ChunkSlot) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_ovf_count.p, 0, 4, ctx->stream));
@@ -403,8 +400,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         aa.order = ctx->d_order.as<int32_t>() + sb.first; aa.n = sb.count; aa.items = ctx->d_items.as<ItemDesc>();
         aa.ref_codes = ctx->d_ref.as<uint8_t>(); aa.seq_codes = ctx->d_seq.as<uint8_t>();
         aa.raw_ref = ctx->d_raw_ref.as<uint8_t>(); aa.raw_seq = ctx->d_raw_seq.as<uint8_t>();
-        aa.nf_ref = ctx->d_nf_ref.as<int32_t>(); aa.lf_ref = ctx->d_lf_ref.as<int32_t>();
-        aa.nf_seq = ctx->d_nf_seq.as<int32_t>(); aa.lf_seq = ctx->d_lf_seq.as<int32_t>();
         aa.colrec = ctx->d_colrec.as<uint4>(); aa.relaid = ctx->d_relaid.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
         aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.np_dim = ctx->P.np_dim; aa.np_clamp = ctx->P.np_clamp;
         CU(cudaEventRecord(e0, ctx->stream));
@@ -561,23 +556,22 @@ int npore_get_np_info(npore_ctx *ctx, const uint8_t *codes, int32_t len, int32_t
     if (!ctx || len < 0 || (len && (!codes || !out))) return NPORE_ERR_BAD_ARG;
     if (len == 0) return NPORE_OK;
     CU(cudaSetDevice(ctx->device));
-    DevBuf d_s, d_raw, d_nf, d_lf, d_out;
+    DevBuf d_s, d_raw, d_out;
     const size_t ob = (size_t)len * 2 * ctx->P.max_n * sizeof(int32_t);
     int rc = NPORE_OK;
-    if (d_s.ensure(len) != cudaSuccess || d_raw.ensure((size_t)len * 8) != cudaSuccess || d_nf.ensure((size_t)len * 4) != cudaSuccess ||
-        d_lf.ensure((size_t)len * 4) != cudaSuccess || d_out.ensure(std::max<size_t>(ob, 4)) != cudaSuccess) rc = fail(ctx, NPORE_ERR_OOM, "np_info scratch");
+    if (d_s.ensure(len) != cudaSuccess || d_raw.ensure((size_t)len * 8) != cudaSuccess || d_out.ensure(std::max<size_t>(ob, 4)) != cudaSuccess)
+        rc = fail(ctx, NPORE_ERR_OOM, "np_info scratch");
     if (rc == NPORE_OK) {
         cudaError_t e = cudaMemcpyAsync(d_s.p, codes, len, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) {
-            np_info_kernel<<<1, ANN_THREADS, 0, ctx->stream>>>(d_s.as<uint8_t>(), len, ctx->P.max_n, ctx->P.max_l, d_raw.as<uint8_t>(),
-                                                               d_nf.as<int32_t>(), d_lf.as<int32_t>(), d_out.as<int32_t>());
+            np_info_kernel<<<1, ANN_THREADS, 0, ctx->stream>>>(d_s.as<uint8_t>(), len, ctx->P.max_n, ctx->P.max_l, d_raw.as<uint8_t>(), d_out.as<int32_t>());
             e = cudaGetLastError();
         }
         if (e == cudaSuccess && ob) e = cudaMemcpyAsync(out, d_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, NPORE_ERR_CUDA, "np_info", e);
     }
-    d_s.release(); d_raw.release(); d_nf.release(); d_lf.release(); d_out.release();
+    d_s.release(); d_raw.release(); d_out.release();
     return rc;
 }
 
