@@ -17,14 +17,16 @@
 //                      holds what the SHR gather of a cell in column j needs from columns j-1..j-6.  Only the
 //                      rare generic path of the forward kernel reads it.
 //   colrec[j] (uint4): .x/.y = the first two SHR candidate descriptors of column j, period n descending (0 = none):
-//                        [2:4] n  [5:11] L  [19:31] (byte offset of the source cell in the forward kernel's history ring)>>2
-//                        = ring row (-n mod 8), array (0 = MAT value if the source column starts the tract, L_IDX==0;
-//                        1 = carried SHR run-start value otherwise), slot (j-n) mod NC          (see forward.cuh)
+//                        [0:2] n  [3:9] L  [10:19] score-table row (n-1)*T + min(L, clamp) (only when NC <= 128)
+//                        [20:31] (NC <= 128; [19:31] for NC = 256) (byte offset of the source cell in the forward
+//                        kernel's history ring)>>2 = ring row (-n mod 8), array (0 = MAT value if the source column
+//                        starts the tract, L_IDX==0; 1 = carried SHR run-start value otherwise), slot (j-n) mod NC
 //                      .z = [0] generic path (more than two SHR candidates or more than one LEN-eligible period; then
-//                           .x/.y/.w are 0)  [1] k-mer contains N  [2:4] base ref[j-1]  [20:31] 2-bit k-mer ref[j..j+5]
-//                      .w = LEN descriptor of the single LEN-eligible period at j: [2:4] n  [5:11] L  [19:31] ring row offset>>2
-//   rowrec[i] (uint32): [4] k-mer contains N  [5:7] base seq[i-1]  [8:13] tract present at i-n (bit 7+n)
-//                       [14:19] tract start at i-n (bit 13+n)  [20:31] 2-bit k-mer seq[i..i+5]   (bits 0-3 are 0)
+//                           .x/.y/.w are 0)  [1] k-mer contains N  [2:4] base ref[j-1]  [8:19] 2-bit k-mer ref[j..j+5]
+//                      .w = LEN descriptor of the single LEN-eligible period at j: [0:2] n  [3:9] L  [10:19] table row
+//                           [20:25] one-hot period mask aligned with rowrec's "tract present" bits (bit 19+n)
+//   rowrec[i] (uint32): [4] k-mer contains N  [5:7] base seq[i-1]  [8:19] 2-bit k-mer seq[i..i+5]
+//                       [20:25] tract present at i-n (bit 19+n)  [26:31] tract start at i-n (bit 25+n, L_IDX==0)
 #pragma once
 #include "common.cuh"
 
@@ -141,15 +143,16 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                         // byte offset inside one warp's ring [NP_RING][4 arrays][NC] floats
                         const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + ((b & 0x80u) ? 0u : (uint32_t)(NC * 4)) +
                                            (uint32_t)((j - n) & (NC - 1)) * 4u;
-                        const uint32_t d = ((uint32_t)n << 2) | (L << 5) | ((F >> 2) << 19);
+                        const uint32_t trow = (uint32_t)((n - 1) * a.np_dim + min((int)L, a.np_clamp));
+                        const uint32_t d = (uint32_t)n | (L << 3) | (NC <= 128 ? (trow << 10) | ((F >> 2) << 20) : ((F >> 2) << 19));
                         if (nshr == 0) w.x = d; else if (nshr == 1) w.y = d;
                         nshr++;
                     }
                     const uint32_t o = raw_byte(raw, len, j, n);
                     if ((o & 0x7fu) && (o & 0x80u)) {
                         lenm |= 1u << (n - 1);
-                        const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16);
-                        w.w = ((uint32_t)n << 2) | ((o & 0x7fu) << 5) | ((F >> 2) << 19);
+                        const uint32_t Lo = o & 0x7fu;
+                        w.w = (uint32_t)n | (Lo << 3) | ((uint32_t)((n - 1) * a.np_dim + min((int)Lo, a.np_clamp)) << 10) | (1u << (19 + n));
                         nlen++;
                     }
                 }
@@ -159,7 +162,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                 const uint32_t km = kmer2_of(s, len, j, hasN);
                 const bool more = nshr > 2 || nlen > 1;
                 if (more) { w.x = w.y = w.w = 0u; }
-                w.z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (km << 20);
+                w.z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (km << 8);
             }
             out[j] = w;
             rel[j] = v;
@@ -176,13 +179,13 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
 #pragma unroll
                 for (int n = 1; n <= NP_MAXN; n++) {
                     const uint32_t b = raw_byte(raw, len, i - n, n);
-                    if (b & 0x7fu) v |= 1u << (7 + n);
-                    if (b & 0x80u) v |= 1u << (13 + n);
+                    if (b & 0x7fu) v |= 1u << (19 + n);
+                    if (b & 0x80u) v |= 1u << (25 + n);
                 }
                 const uint32_t base = (i >= 1 && i - 1 < len) ? s[i - 1] : 0u;
                 uint32_t hasN = 0;
                 const uint32_t km = kmer2_of(s, len, i, hasN);
-                v |= hasN << 4 | (base & 7u) << 5 | km << 20;
+                v |= hasN << 4 | (base & 7u) << 5 | km << 8;
             }
             out[i] = v;
         }

@@ -184,9 +184,15 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     ctx->cpl = W <= 32 ? 1 : W <= 64 ? 2 : W <= 128 ? 4 : 8;
     ctx->tbs = np_tbs(ctx->cpl);
     if (ctx->d_sub.ensure(25 * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
-    if (ctx->d_np.ensure((size_t)np_n * np_dim * np_dim * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
+    // score table re-laid with a guard column: np2[row][c] = np_scores[row][c-1], np2[row][0] = 100.0 (forward.cuh)
+    std::vector<float> np2((size_t)np_n * np_dim * (np_dim + 1));
+    for (int64_t row = 0; row < (int64_t)np_n * np_dim; row++) {
+        np2[(size_t)row * (np_dim + 1)] = 100.0f;
+        memcpy(&np2[(size_t)row * (np_dim + 1) + 1], np_scores + row * np_dim, sizeof(float) * (size_t)np_dim);
+    }
+    if (ctx->d_np.ensure(np2.size() * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
     if (cudaMemcpy(ctx->d_sub.p, sub_scores, 25 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NPORE_ERR_CUDA);
-    if (cudaMemcpy(ctx->d_np.p, np_scores, (size_t)np_n * np_dim * np_dim * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
+    if (cudaMemcpy(ctx->d_np.p, np2.data(), np2.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(NPORE_ERR_CUDA);
     if (ctx->d_counter.ensure(64) != cudaSuccess || ctx->d_ovf_count.ensure(64) != cudaSuccess ||
         ctx->d_ovf.ensure(sizeof(OverflowRec) * npore_ctx::OVF_CAP) != cudaSuccess) return bail(NPORE_ERR_OOM);

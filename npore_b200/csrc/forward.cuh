@@ -94,29 +94,37 @@ template <int OFF> __device__ __forceinline__ void sts_u2_off(uint32_t a, uint32
 // History ring of one warp: float ring[NP_RING][4][NC]   (arrays: 0 MAT.VAL, 1 SHR run-start value, 2 LEN run-start
 // value, 3 LEN.RUN | SHR.RUN<<16), NC*128 bytes; a cell is addressed as (offset & mask) + base.
 // One SHR candidate from a pre-decoded descriptor (aln.pyx:642-667 in gather form; annotate.cuh for the fields).
+// One SHR candidate (aln.pyx:642-667 in gather form) from a pre-decoded descriptor (annotate.cuh).  Straight-line code:
+// a zero descriptor reads valid dummy locations and is rejected by `pred`.  np2 is the score table re-laid with one
+// guard column: np2[row][c] = np_scores[row][c-1], np2[row][0] = 100.0 (np_score()'s "ref_l + indel < 0" answer,
+// aln.pyx:262-263), row stride T2 = T+1, so the clamp of aln.pyx:269-272 and the guard are one DPX instruction.
 template <int NC>
 __device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, uint32_t wbase, uint32_t lutbase, int bc, uint32_t sip,
-                                         const float *__restrict__ np, int T, int cl, float &Sv, int &Sr, float &Sb)
+                                         const float *__restrict__ np2, int T2, int cl1, float &Sv, int &Sr, float &Sb)
 {
-    // straight-line (no branch): a zero descriptor reads valid dummy locations and is rejected by `pred`
-    const uint32_t f = (D >> 17) + dsh;
+    constexpr bool TROW = NC <= 128;
+    const uint32_t f = (D >> (TROW ? 18 : 17)) + dsh;
     const uint32_t a = FWD_ADDR(f & (uint32_t)(NC * 128 - 4), wbase);
     const float base = lds_f(a);
     const uint32_t rr = lds_u_off<NC * 8>(a);                         // array + 2: run word when base is array 1
-    const uint32_t n4 = D & 0x1cu;
-    const uint2 lut = lds_u2(lutbase + n4 * 2u);                      // {ceil(2^31/n), (n-1)*T*T}
-    const bool start = (D & ((uint32_t)NC << 19)) == 0u;              // array bit of the descriptor offset field
+    const uint32_t n = D & 7u, n4 = n << 2;
+    const bool start = (D & ((uint32_t)NC << (TROW ? 20 : 19))) == 0u;  // array bit of the descriptor offset field
     const int run0 = start ? 0 : (int)(rr >> 16);
     const bool ok = pred && (bc > (int)((sip >> n4) & 7u)) && (start || run0 > 0);
-    const int q = (int)__umulhi((uint32_t)run0 << 1, lut.x);
-    const int L = (int)((D >> 5) & 0x7fu);
-    const int call = L - q - 1;
-    const uint32_t idx = lut.y + (uint32_t)(min(L, cl) * T) + (uint32_t)max(min(call, cl), 0);
-    float sc = __ldg(np + idx);
-    sc = call >= 0 ? sc : 100.f;
-    const float cand = base + sc;
+    const int L = (int)((D >> 3) & 0x7fu);
+    uint32_t idx;
+    if (TROW) {
+        const uint32_t magic = lds_u_off<0>(lutbase + n4 * 2u);
+        const int q = (int)__umulhi((uint32_t)run0 << 1, magic);
+        idx = ((D >> 10) & 0x3ffu) * (uint32_t)T2 + (uint32_t)__vimin_s32_relu(L - q, cl1);
+    } else {
+        const uint2 lut = lds_u2(lutbase + n4 * 2u);                  // {ceil(2^31/n), (n-1)*T}
+        const int q = (int)__umulhi((uint32_t)run0 << 1, lut.x);
+        idx = (lut.y + (uint32_t)min(L, cl1 - 1)) * (uint32_t)T2 + (uint32_t)__vimin_s32_relu(L - q, cl1);
+    }
+    const float cand = base + __ldg(np2 + idx);
     const bool better = ok && cand < Sv;
-    Sv = better ? cand : Sv; Sr = better ? min(run0 + (int)(n4 >> 2), NP_RUN_SAT) : Sr; Sb = better ? base : Sb;
+    Sv = better ? cand : Sv; Sr = better ? __viaddmin_s32(run0, (int)n, NP_RUN_SAT) : Sr; Sb = better ? base : Sb;
 }
 
 #ifndef FWD_MINB
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
     }
     if (threadIdx.x < 8) {
         const uint32_t n = threadIdx.x;
-        s_lut[n] = make_uint2(n >= 1 ? (uint32_t)((0x80000000ull + n - 1) / n) : 0u, n >= 1 ? (n - 1) * a.P.np_dim * a.P.np_dim : 0u);
+        s_lut[n] = make_uint2(n >= 1 ? (uint32_t)((0x80000000ull + n - 1) / n) : 0u, n >= 1 ? (n - 1) * a.P.np_dim : 0u);
     }
     __syncthreads();
 #if FWD_ALIGNED
@@ -160,10 +168,10 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
     const uint32_t lutbase = (uint32_t)__cvta_generic_to_shared(s_lut);
     const uint32_t myslot4 = (uint32_t)(lane * CPL) * 4u;
 
-    const int r = a.P.r, T = a.P.np_dim, cl = a.P.np_clamp;
+    const int r = a.P.r, T2 = a.P.np_dim + 1, cl1 = a.P.np_clamp + 1;
     const float gopen = a.P.gap_open, gext = a.P.gap_ext;
-    const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 8;       // rowrec "present" bits live at [8:13]
-    const float *__restrict__ np = a.np_tab;
+    const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 20;      // rowrec "present" bits live at [20:25]
+    const float *__restrict__ np = a.np_tab;          // re-laid table with guard column (api.cu)
     const int src_lane = (lane + 31) & 31;
 
     for (;;) {
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             bool in[CPL];
             float Sv[CPL], Sb[CPL], Lv[CPL], Lb[CPL]; int Sr[CPL], Lr[CPL];
             bool p0[CPL], p1[CPL], pg[CPL], pl[CPL];
-            bool any1 = false, anyg = false, anyl = false;
+            uint32_t any1 = 0u, anyg = 0u, anyl = 0u;      // warp votes on plain ORs of the raw words (slightly conservative)
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 in[k] = (unsigned)(bc[k] - lo) <= span && hi >= lo;
@@ -269,47 +277,47 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 p0[k] = in[k] && cc[k].x != 0u;
                 p1[k] = in[k] && cc[k].y != 0u;
                 pg[k] = in[k] && (cc[k].z & 1u);
-                pl[k] = in[k] && (((rw[k] & nmask) >> (((cc[k].w >> 2) & 7u) + 7u)) & 1u);   // rowrec bit 7 is always 0
-                any1 |= p1[k]; anyg |= pg[k]; anyl |= pl[k];
+                const uint32_t lw = rw[k] & cc[k].w & nmask;               // one-hot LEN period vs "tract present" bits
+                pl[k] = in[k] && lw != 0u;
+                any1 |= cc[k].y; anyg |= cc[k].z; anyl |= lw;
             }
             // ---- SHR gather: descriptor 0 (largest period; some lane almost always has one), then descriptor 1
 #pragma unroll
-            for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].x, p0[k], dsh, wbase, lutbase, bc[k], sip, np, T, cl, Sv[k], Sr[k], Sb[k]);
-            if (__any_sync(NP_FULL, any1)) {
+            for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].x, p0[k], dsh, wbase, lutbase, bc[k], sip, np, T2, cl1, Sv[k], Sr[k], Sb[k]);
+            if (__any_sync(NP_FULL, any1 != 0u)) {
 #pragma unroll
-                for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].y, p1[k], dsh, wbase, lutbase, bc[k], sip, np, T, cl, Sv[k], Sr[k], Sb[k]);
+                for (int k = 0; k < CPL; k++) shr_eval<NC>(cc[k].y, p1[k], dsh, wbase, lutbase, bc[k], sip, np, T2, cl1, Sv[k], Sr[k], Sb[k]);
             }
             // ---- LEN gather (aln.pyx:602-633): single eligible period, 2-bit k-mer unit compare in registers
-            if (__any_sync(NP_FULL, anyl)) {
+            if (__any_sync(NP_FULL, anyl != 0u)) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
                     if (pl[k]) {
                         const uint32_t D = cc[k].w;
                         if ((cc[k].z | (rw[k] >> 3)) & 2u) {
-                            pg[k] = true; anyg = true;             // an N inside a k-mer: byte-wise compare on the generic path
+                            pg[k] = true; anyg |= 1u;              // an N inside a k-mer: byte-wise compare on the generic path
                         } else {
-                            const uint32_t n4 = D & 0x1cu;
-                            const int n = (int)(n4 >> 2);
-                            const bool eq = (((cc[k].z ^ rw[k]) >> 20) << (32 - 2 * n)) == 0u;
-                            const bool start = ((rw[k] >> (13 + n)) & 1u) != 0u;
-                            const uint32_t f = (D >> 17) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
+                            const int n = (int)(D & 7u);
+                            const uint32_t n4 = (uint32_t)n << 2;
+                            const bool eq = ((((cc[k].z ^ rw[k]) >> 8) << (32 - 2 * n)) == 0u);
+                            const bool start = ((rw[k] >> (25 + n)) & 1u) != 0u;
+                            const uint32_t f = (uint32_t)((-n) & (NP_RING - 1)) * (uint32_t)(NC * 16) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
                             const uint32_t ad = FWD_ADDR(f & (uint32_t)(NC * 128 - 4), wbase);
                             const float base = lds_f(ad);
                             const uint32_t rr = lds_u_off<NC * 4>(ad);                 // array 2 + 1 = run word
-                            const uint2 lut = lds_u2(lutbase + n4 * 2u);
+                            const uint32_t magic = lds_u_off<0>(lutbase + n4 * 2u);
                             const int run0 = start ? 0 : (int)(rr & 0xffffu);
                             const bool ok = eq && (bc[k] + n - (int)((sip >> n4) & 7u) <= 2 * r - 1) && (start || run0 > 0);
-                            const int q = (int)__umulhi((uint32_t)run0 << 1, lut.x);
-                            const int L = (int)((D >> 5) & 0x7fu);
-                            const int call = L + q + 1;
-                            const float cand = base + __ldg(np + (lut.y + (uint32_t)(min(L, cl) * T) + (uint32_t)min(call, cl)));
+                            const int q = (int)__umulhi((uint32_t)run0 << 1, magic);
+                            const int L = (int)((D >> 3) & 0x7fu);
+                            const float cand = base + __ldg(np + (((D >> 10) & 0x3ffu) * (uint32_t)T2 + (uint32_t)min(L + q + 2, cl1)));
                             if (ok && cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + n, NP_RUN_SAT); Lb[k] = base; }
                         }
                     }
                 }
             }
             // ---- generic path (rare): all periods from the relaid byte record in global memory
-            if (__any_sync(NP_FULL, anyg)) {
+            if (__any_sync(NP_FULL, (anyg & 1u) != 0u)) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
                     if (pg[k]) {
@@ -322,11 +330,12 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                                 if (!L) continue;
                                 const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + ((byte & 0x80u) ? 0u : (uint32_t)(NC * 4)) +
                                                    (uint32_t)((j - n) & (NC - 1)) * 4u;
-                                const uint32_t D = ((uint32_t)n << 2) | (L << 5) | ((F >> 2) << 19);
-                                shr_eval<NC>(D, true, dsh, wbase, lutbase, bc[k], sip, np, T, cl, Sv[k], Sr[k], Sb[k]);
+                                const uint32_t trow = (uint32_t)((n - 1) * (T2 - 1) + min((int)L, cl1 - 1));
+                                const uint32_t D = (uint32_t)n | (L << 3) | (NC <= 128 ? (trow << 10) | ((F >> 2) << 20) : ((F >> 2) << 19));
+                                shr_eval<NC>(D, true, dsh, wbase, lutbase, bc[k], sip, np, T2, cl1, Sv[k], Sr[k], Sb[k]);
                             }
                         }
-                        uint32_t lm = (rb.y >> 22) & ((rw[k] & nmask) >> 8) & 0x3fu;   // LEN, every eligible period
+                        uint32_t lm = (rb.y >> 22) & ((rw[k] & nmask) >> 20) & 0x3fu;   // LEN, every eligible period
                         while (lm) {
                             const int n = 32 - __clz(lm);
                             lm &= ~(1u << (n - 1));
@@ -338,14 +347,14 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                             if (!eq) continue;
                             const uint2 cjn = rel[j + n];
                             const int L = (int)(((n <= 4 ? cjn.x : cjn.y) >> ((8 * (n - 1)) & 31)) & 0x7fu);
-                            const bool start = ((rw[k] >> (13 + n)) & 1u) != 0u;
+                            const bool start = ((rw[k] >> (25 + n)) & 1u) != 0u;
                             const uint32_t f = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
                             const uint32_t ad = FWD_ADDR(f & (uint32_t)(NC * 128 - 4), wbase);
                             const float base = lds_f(ad);
                             const int run0 = start ? 0 : (int)(lds_u_off<NC * 4>(ad) & 0xffffu);
                             if (!start && run0 <= 0) continue;
                             const int call = L + run0 / n + 1;
-                            const float cand = base + __ldg(np + ((n - 1) * T + min(L, cl)) * T + min(call, cl));
+                            const float cand = base + __ldg(np + ((n - 1) * (T2 - 1) + min(L, cl1 - 1)) * T2 + min(call + 1, cl1));
                             if (cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + n, NP_RUN_SAT); Lb[k] = base; }
                         }
                     }
@@ -359,17 +368,17 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             for (int k = 0; k < CPL; k++) {
                 // INS from top = own previous value; DEL from left.  Only the "extended" bits are kept (see common.cuh)
                 const float iv1 = Mv1[k] + gopen, iv2 = Iv1[k] + gext;
-                bool ie = iv2 < iv1;
-                Iv[k] = ie ? iv2 : iv1;
+                Iv[k] = fminf(iv1, iv2);                                             // equal on ties: either operand is the value
+                uint32_t ieb = __float_as_uint(iv2 - iv1);                           // sign bit set <=> iv2 < iv1 (aln.pyx:536)
                 const float dv1 = lMv[k] + gopen, dv2 = lDv[k] + gext;
-                bool de = dv2 < dv1;
-                Dv[k] = de ? dv2 : dv1;
+                Dv[k] = fminf(dv1, dv2);
+                uint32_t deb = __float_as_uint(dv2 - dv1);                           // aln.pyx:558
                 uint32_t pk = (uint32_t)min(dgr[k] + 1, NP_RUN_SAT);                 // typ MAT = 0
                 float best = dgv[k] + lds_f(subbase + (rw[k] & 0xe0u) + (cc[k].z & 0x1cu));
                 if (!steady) {
                     const int i = Id + r - bc[k], j = Dd - r + bc[k];
-                    if (i <= 1) ie = false;                                          // aln.pyx:537-538 (run restarts), :525-528
-                    if (j <= 1) de = false;                                          // aln.pyx:559-560, :547-550
+                    if (i <= 1) ieb = 0u;                                            // aln.pyx:537-538 (run restarts), :525-528
+                    if (j <= 1) deb = 0u;                                            // aln.pyx:559-560, :547-550
                     if (i == 0) Iv[k] = (float)(100 * (j + 1));
                     if (j == 0) Dv[k] = (float)(100 * (i + 1));
                     if (!(i > 0 && j > 0)) { best = Dv[k] + 100.f; pk = 0u; }
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 Iv[k] = in[k] ? Iv[k] : edgev;
                 Dv[k] = in[k] ? Dv[k] : edgev;
                 Mr[k] = (in[k] && pk < (1u << NP_REC_TYP)) ? (int)pk : 0;
-                recs[k] = in[k] ? (pk | (ie ? NP_REC_IE : 0u) | (de ? NP_REC_DE : 0u)) : 0u;
+                recs[k] = in[k] ? (pk | ((ieb >> 20) & NP_REC_IE) | ((deb >> 19) & NP_REC_DE)) : 0u;
             }
 
             // ---- history ring [ring][array][slot] + traceback row (slot order)
