@@ -124,6 +124,7 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, FWD_WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
+    ctx->stats.overflow_runs = per_sm * FWD_WARPS;      // resident forward warps per SM (diagnostic)
     int grid = std::min((n_sub + FWD_WARPS - 1) / FWD_WARPS, ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
     forward_kernel<CPL><<<grid, FWD_WARPS * 32, smem, ctx->stream>>>(fa);
@@ -503,7 +504,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     S.n_sub_batches = (int)ctx->subs.size();
     int ovf = 0;
     CU(cudaMemcpy(&ovf, ctx->d_ovf_count.p, 4, cudaMemcpyDeviceToHost));
-    S.overflow_runs = ovf;
     if (ovf > npore_ctx::OVF_CAP) return fail(ctx, NPORE_ERR_CAPACITY, "run-overflow list exhausted");
     ctx->ran = true;
     return NPORE_OK;
