@@ -73,7 +73,8 @@ struct npore_ctx {
     DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
         d_item_len, d_item_status, d_rleA, d_rleB, d_rle_len, d_rle_which, d_ops_off, d_rle_off, d_pack_ops, d_pack_rle, d_order, d_slots, d_counter, d_ovf, d_ovf_count;
     // per sub-batch scratch
-    DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_tb;
+    DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_tb, d_rr_q, d_rr_ctl, d_rr_state;
+    int rr_slice = 512;
     HostBuf h_small;
     int64_t pack_ops_total = 0, pack_rle_total = 0;
     std::vector<ItemDesc> items;
@@ -203,6 +204,7 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     if (cudaGetLastError() != cudaSuccess) return bail(NPORE_ERR_CUDA);
     ctx->scratch_budget = (size_t)((double)fr * 0.55);
     if (const char *s = getenv("NPORE_SCRATCH_MB")) ctx->scratch_budget = (size_t)atoll(s) << 20;
+    if (const char *s = getenv("NPORE_RR_SLICE")) ctx->rr_slice = std::max(8, atoi(s));
     *out = ctx;
     return NPORE_OK;
 }
@@ -214,7 +216,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
                       &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
-                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb};
+                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
     for (auto *b : bufs) b->release();
     ctx->h_small.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -383,6 +385,13 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     CU(ctx->d_colrec.ensure(max_col * 16 + 64)); CU(ctx->d_relaid.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
     CU(ctx->d_rowrec.ensure(max_row * 4 + 64)); CU(ctx->d_raw_seq.ensure(max_row * 8 + 64));
     CU(ctx->d_tb.ensure(max_tb * (size_t)(64 * ctx->tbs) + 256));
+    int max_sub = 1;
+    for (const SubBatch &sb : ctx->subs) max_sub = std::max(max_sub, sb.count);
+    int rr_cap = 1;
+    while (rr_cap < 2 * max_sub + 16384) rr_cap <<= 1;
+    CU(ctx->d_rr_q.ensure(sizeof(int) * (size_t)rr_cap));
+    CU(ctx->d_rr_ctl.ensure(64));
+    CU(ctx->d_rr_state.ensure(sizeof(uint32_t) * fwd_rr_state_words(ctx->cpl) * (size_t)max_sub));
     if (nchunks) CU(cudaMemcpyAsync(ctx->d_slots.p, ctx->slots.data(), sizeof(ChunkSlot) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_ovf_count.p, 0, 4, ctx->stream));
 
@@ -422,6 +431,13 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         fa.out = ctx->d_chunk_out.as<ChunkOut>();
         fa.ovf = ctx->d_ovf.as<OverflowRec>(); fa.ovf_count = ctx->d_ovf_count.as<int>(); fa.ovf_cap = npore_ctx::OVF_CAP;
         fa.P = ctx->P;
+        fa.rr_q = ctx->d_rr_q.as<int>(); fa.rr_mask = rr_cap - 1; fa.rr_ctl = ctx->d_rr_ctl.as<int>();
+        fa.rr_state = ctx->d_rr_state.as<uint32_t>(); fa.rr_slice = ctx->rr_slice;
+#if FWD_RR
+        CU(cudaMemsetAsync(ctx->d_rr_state.p, 0, sizeof(uint32_t) * fwd_rr_state_words(ctx->cpl) * (size_t)sb.count, ctx->stream));
+        rr_init_kernel<<<64, 256, 0, ctx->stream>>>(fa.rr_q, rr_cap, sb.count, fa.rr_ctl);
+        CU(cudaGetLastError()); S.launches++;
+#endif
         CU(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
         int rc = NPORE_OK;
         switch (ctx->cpl) {

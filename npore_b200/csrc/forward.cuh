@@ -59,8 +59,25 @@ struct ForwardArgs {
     const float *sub_tab;         // [5][5]  indexed [seq_base][ref_base]
     ChunkOut *out;                // indexed by chunk id
     OverflowRec *ovf; int *ovf_count; int ovf_cap;
+    // round-robin time slicing (FWD_RR): run queue + per-chunk saved state
+    int *rr_q; int rr_mask; int *rr_ctl;      // ctl[0] head, ctl[1] tail, ctl[2] finished chunks
+    uint32_t *rr_state; int rr_slice;
     AlignParams P;
 };
+
+#ifndef FWD_RR
+#define FWD_RR 1
+#endif
+// words of saved per-lane state per cell: Mv1 Iv1 Dv1 dgv Mr1 dgr cc(4) rw
+#define FWD_RR_WORDS 11
+#define FWD_RR_HDR 32      // uint32 words: d, Id, Dd, hist
+static __host__ __device__ inline size_t fwd_rr_state_words(int cpl) { return (size_t)FWD_RR_HDR + (size_t)FWD_RR_WORDS * cpl * 32 + (size_t)32 * cpl * 32; }
+
+__global__ void rr_init_kernel(int *q, int cap, int n, int *ctl)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) q[i] = i < n ? i : -1;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[0] = 0; ctl[1] = n; ctl[2] = 0; }
+}
 
 // #I among the last n ops (n = 1..6) for every 6-bit op history, packed 4 bits per n at nibble n
 __constant__ uint32_t c_sipack[64];
@@ -176,12 +193,39 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
 
     for (;;) {
         int idx = 0;
+#if FWD_RR
+        {   // pop the next runnable chunk (FIFO); wait for a push if the queue is momentarily empty
+            int pos = 0;
+            if (lane == 0) {
+                pos = atomicAdd(a.rr_ctl, 1);
+                volatile int *qp = a.rr_q + (pos & a.rr_mask);
+                int v;
+                while ((v = *qp) < 0) {
+                    if (*(volatile int *)(a.rr_ctl + 2) >= a.n) { v = -2; break; }
+                    __nanosleep(256);
+                }
+                if (v >= 0) *qp = -1;
+                idx = v;
+            }
+            idx = __shfl_sync(NP_FULL, idx, 0);
+            if (idx < 0) break;
+        }
+#else
         if (lane == 0) idx = atomicAdd(a.counter, 1);
         idx = __shfl_sync(NP_FULL, idx, 0);
         if (idx >= a.n) break;
+#endif
         const int cid = a.order[idx];
         const ChunkDesc c = a.chunks[cid];
-        if (!c.valid) { if (lane == 0) a.out[cid].score = 0.f; continue; }
+        if (!c.valid) {
+            if (lane == 0) {
+                a.out[cid].score = 0.f;
+#if FWD_RR
+                atomicAdd(a.rr_ctl + 2, 1);
+#endif
+            }
+            continue;
+        }
         const ChunkSlot sl = a.slots[idx];
         const ItemDesc &I = a.items[c.item];
         const uint32_t *__restrict__ bits = a.bits + I.bit_word_off;
@@ -207,15 +251,45 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             cc[k] = (j0 > 0) ? col[j0] : (j0 == -r ? col[NC - r] : make_uint4(0u, 0u, 0u, 0u));
             if (j0 == 0) cc[k] = col[0];
         }
-        uint32_t nrow = row[r + 1];                          // next row to enter the band (at b_col == 0)
-        int wbase_w = c.brk >> 5; uint32_t wbuf = bits[wbase_w + lane];
+        int d0 = 0; uint32_t hist = 0; int Id = 0, Dd = 0;
+#if FWD_RR
+        uint32_t *st = a.rr_state + (size_t)idx * fwd_rr_state_words(CPL);
+        d0 = (int)__ldcg(st);
+        if (d0 > 0) {     // resume: scalars, per-lane registers, history ring
+            Id = (int)__ldcg(st + 1); Dd = (int)__ldcg(st + 2); hist = __ldcg(st + 3);
+            const uint32_t *sp = st + FWD_RR_HDR + lane;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                const uint32_t *q = sp + (size_t)k * FWD_RR_WORDS * 32;
+                Mv1[k] = __uint_as_float(__ldcg(q)); Iv1[k] = __uint_as_float(__ldcg(q + 32)); Dv1[k] = __uint_as_float(__ldcg(q + 64));
+                dgv[k] = __uint_as_float(__ldcg(q + 96)); Mr1[k] = (int)__ldcg(q + 128); dgr[k] = (int)__ldcg(q + 160);
+                cc[k] = make_uint4(__ldcg(q + 192), __ldcg(q + 224), __ldcg(q + 256), __ldcg(q + 288));
+                rw[k] = __ldcg(q + 320);
+                bc[k] = (lane * CPL + k + r - Dd) & (NC - 1);
+            }
+            const uint4 *rp = reinterpret_cast<const uint4 *>(st + FWD_RR_HDR + (size_t)FWD_RR_WORDS * CPL * 32);
+#pragma unroll
+            for (int t = 0; t < NC / 4; t++) {
+                const uint4 v = __ldcg(rp + t * 32 + lane);
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(wbase + (uint32_t)(t * 32 + lane) * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+            __syncwarp();
+        }
+#endif
+        uint32_t nrow = row[Id + r + 1];                     // next row to enter the band (at b_col == 0)
+        const int g00 = c.brk + (d0 > 0 ? d0 - 1 : 0);
+        int wbase_w = g00 >> 5; uint32_t wbuf = bits[wbase_w + lane];
         uint32_t cw = __shfl_sync(NP_FULL, wbuf, 0);
-        uint32_t hist = 0; int Id = 0, Dd = 0;
-        float infd = 0.f;                                     // 100*d, exact in fp32 (d < 2^16)
+        float infd = (float)(100 * (d0 > 0 ? d0 - 1 : 0));   // 100*d, exact in fp32 (d < 2^16); advanced at the top of a step
         // steady state = every cell with 1 <= b_col <= 2r-1 is an interior cell with i >= 2 and j >= 2
         const int idLo = r + 1, idSpan = imax - 2 * r, ddSpan = jmax - 2 * r;
+#if FWD_RR
+        const int dEnd = min(B, d0 + a.rr_slice);
+#else
+        const int dEnd = B;
+#endif
 
-        for (int d = 0; d < B; d++) {
+        for (int d = d0; d < dEnd; d++) {
             float lMv[CPL], lDv[CPL]; int lMr[CPL];
             if (d > 0) {
                 const int g = c.brk + d - 1;                 // op that leads to this anti-diagonal
@@ -429,10 +503,41 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 Mv1[k] = Mv[k]; Iv1[k] = Iv[k]; Dv1[k] = Dv[k]; Mr1[k] = Mr[k];
             }
         }
+#if FWD_RR
+        if (dEnd < B) {     // slice over: save the chunk's state and hand it back to the run queue
+            uint32_t *sp = st + FWD_RR_HDR + lane;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                uint32_t *q = sp + (size_t)k * FWD_RR_WORDS * 32;
+                __stcg(q, __float_as_uint(Mv1[k])); __stcg(q + 32, __float_as_uint(Iv1[k])); __stcg(q + 64, __float_as_uint(Dv1[k]));
+                __stcg(q + 96, __float_as_uint(dgv[k])); __stcg(q + 128, (uint32_t)Mr1[k]); __stcg(q + 160, (uint32_t)dgr[k]);
+                __stcg(q + 192, cc[k].x); __stcg(q + 224, cc[k].y); __stcg(q + 256, cc[k].z); __stcg(q + 288, cc[k].w);
+                __stcg(q + 320, rw[k]);
+            }
+            uint4 *rp = reinterpret_cast<uint4 *>(st + FWD_RR_HDR + (size_t)FWD_RR_WORDS * CPL * 32);
+#pragma unroll
+            for (int t = 0; t < NC / 4; t++) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(wbase + (uint32_t)(t * 32 + lane) * 16u));
+                __stcg(rp + t * 32 + lane, v);
+            }
+            if (lane == 0) { __stcg(st, (uint32_t)dEnd); __stcg(st + 1, (uint32_t)Id); __stcg(st + 2, (uint32_t)Dd); __stcg(st + 3, hist); }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) {
+                const int p2 = atomicAdd(a.rr_ctl + 1, 1);
+                *(volatile int *)(a.rr_q + (p2 & a.rr_mask)) = idx;
+            }
+            continue;
+        }
+#endif
         // chunk score = MAT value of the end cell (b_col == r on the last anti-diagonal)
 #pragma unroll
         for (int k = 0; k < CPL; k++)
             if (bc[k] == r) a.out[cid].score = Mv1[k];
         __syncwarp();
+#if FWD_RR
+        if (lane == 0) { __threadfence(); atomicAdd(a.rr_ctl + 2, 1); }
+#endif
     }
 }
