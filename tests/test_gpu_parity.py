@@ -292,3 +292,22 @@ def test_realign_reads_streams_in_batches(tables, tmp_path):
     for rd, line in zip(reads, lines):
         assert line.split("\t")[5] == oracle.realign_cigar(rd[9], rd[7], rd[5], S, NP)
     assert cfg.counter.value >= 40
+
+
+def test_round_robin_time_slicing(tables, golden):
+    """forward_kernel hands chunks back to the run queue every NPORE_RR_SLICE anti-diagonals (state saved to HBM and
+    resumed by whichever warp pops it next): results must not depend on the slice length."""
+    from npore_b200.engine import Realigner
+    S, NP = tables
+    cases = [c for c in golden("fuzz.json.gz") if c["r"] == 30 and c["max_b_rows"] == 20000]
+    refs = [oracle.bases_to_int(c["ref"]) for c in cases]; seqs = [oracle.bases_to_int(c["seq"]) for c in cases]
+    for sl in ("8", "37", "100000"):
+        os.environ["NPORE_RR_SLICE"] = sl
+        try:
+            eng = Realigner(S, NP)
+        finally:
+            del os.environ["NPORE_RR_SLICE"]
+        outs, scores, status = eng.align_many(refs, seqs, [c["cigar"] for c in cases])
+        for c, o, sc in zip(cases, outs, scores):
+            assert o == c["out"] and np.array_equal(sc, np.array(c["scores"], np.float32))
+        eng.close()
