@@ -1,0 +1,206 @@
+"""BAM / FASTA / SAM I/O without pysam -- the callers either side of the hot path.
+
+  read_bam(path)                 BGZF inflate + BAM record decode (SAM spec section 4: `<iiBBHHHiiii` core, 4-bit
+                                 `=ACMGRSVTWYHKDBN` bases, `MIDNSHP=XB` op codes)
+  get_read_data(bam, fasta, ..)  generator of the 11-tuples of /root/reference/src/bam.pyx:18-47 (same filters: no
+                                 secondary / supplementary / unmapped; soft clips stripped from SEQ/QUAL like pysam's
+                                 query_alignment_sequence; reference slice = fasta[start:stop].upper(), which is what
+                                 get_reference_sequence().upper() yields)
+  create_header(...)             bam.pyx:127-145: @HD VN:1.6 SO:coordinate, @SQ per contig, @PG realigner
+  write_bam(path, ...)           minimal BGZF/BAM writer (fixtures for the tests; records in input order)
+  realign_bam(...)               ingest -> GPU batches -> ordered SAM: what realign.py:75-115 does end to end
+Host code only; the GPU path is entered through npore_b200.bam.realign_reads.
+"""
+import gzip
+import io
+import os
+import struct
+import sys
+import zlib
+
+import numpy as np
+
+from . import cfg
+
+_SEQ16 = "=ACMGRSVTWYHKDBN"
+_OPS = "MIDNSHP=XB"
+_SEQ_PAIR = np.array([a + b for a in _SEQ16 for b in _SEQ16])
+
+
+def read_fasta(path):
+    """{contig: sequence} (plain or gzip FASTA)."""
+    opener = gzip.open if path.endswith(".gz") else open
+    out, name, parts = {}, None, []
+    with opener(path, "rt") as fh:
+        for line in fh:
+            if line.startswith(">"):
+                if name is not None:
+                    out[name] = "".join(parts)
+                name, parts = line[1:].split()[0], []
+            else:
+                parts.append(line.strip())
+    if name is not None:
+        out[name] = "".join(parts)
+    return out
+
+
+def _parse_tags(buf):
+    tags, p, n = {}, 0, len(buf)
+    sizes = {"A": 1, "c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}
+    fmts = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I", "f": "<f"}
+    while p + 3 <= n:
+        tag, typ = buf[p:p + 2].decode(), chr(buf[p + 2])
+        p += 3
+        if typ == "A":
+            tags[tag] = chr(buf[p]); p += 1
+        elif typ in fmts:
+            tags[tag] = struct.unpack_from(fmts[typ], buf, p)[0]; p += sizes[typ]
+        elif typ in "ZH":
+            e = buf.index(b"\0", p)
+            tags[tag] = buf[p:e].decode(); p = e + 1
+        elif typ == "B":
+            sub = chr(buf[p]); cnt = struct.unpack_from("<i", buf, p + 1)[0]
+            p += 5
+            tags[tag] = list(struct.unpack_from("<" + str(cnt) + fmts[sub][1], buf, p)); p += cnt * sizes[sub]
+        else:
+            break
+    return tags
+
+
+def read_bam(path):
+    """Returns (header_text, [(name, length)], iterator of record dicts).  Whole-file inflate (gzip concatenates the
+    BGZF members); fine for the batch sizes realign handles per call."""
+    with gzip.open(path, "rb") as fh:
+        data = fh.read()
+    if data[:4] != b"BAM\1":
+        raise ValueError(f"{path}: not a BAM file")
+    l_text = struct.unpack_from("<i", data, 4)[0]
+    text = data[8:8 + l_text].split(b"\0")[0].decode()
+    p = 8 + l_text
+    n_ref = struct.unpack_from("<i", data, p)[0]; p += 4
+    refs = []
+    for _ in range(n_ref):
+        l_name = struct.unpack_from("<i", data, p)[0]; p += 4
+        name = data[p:p + l_name - 1].decode(); p += l_name
+        refs.append((name, struct.unpack_from("<i", data, p)[0])); p += 4
+
+    def records(p=p):
+        n = len(data)
+        while p + 4 <= n:
+            block_size = struct.unpack_from("<i", data, p)[0]; p += 4
+            ref_id, pos, l_read_name, mapq, _bin, n_cigar, flag, l_seq, _nref, _npos, _tlen = struct.unpack_from("<iiBBHHHiiii", data, p)
+            q = p + 32
+            name = data[q:q + l_read_name - 1].decode(); q += l_read_name
+            cig = np.frombuffer(data, dtype="<u4", count=n_cigar, offset=q); q += 4 * n_cigar
+            packed = np.frombuffer(data, dtype=np.uint8, count=(l_seq + 1) // 2, offset=q); q += (l_seq + 1) // 2
+            seq = "".join(_SEQ_PAIR[packed])[:l_seq]
+            qual = np.frombuffer(data, dtype=np.uint8, count=l_seq, offset=q); q += l_seq
+            tags = _parse_tags(data[q:p + block_size])
+            yield {"name": name, "flag": flag, "ref_id": ref_id, "pos": pos, "mapq": mapq, "cigar": cig, "seq": seq,
+                   "qual": None if (l_seq and qual[0] == 0xFF) else qual, "tags": tags}
+            p += block_size
+    return text, refs, records()
+
+
+def _cigar_string(words):
+    return "".join(f"{int(w) >> 4}{_OPS[int(w) & 15]}" for w in words)
+
+
+def get_read_data(bam_fn, fasta, regions=None, max_reads=0):
+    """bam.pyx:18-47.  fasta: path or {contig: seq}.  regions: [(contig, start, stop)] or None for everything (a read
+    overlapping two regions is yielded once per region, as pysam's fetch does)."""
+    if not os.path.exists(bam_fn):
+        print(f"\nERROR: BAM file '{bam_fn}' not found.")
+        sys.exit(1)
+    fa = read_fasta(fasta) if isinstance(fasta, str) else fasta
+    _, refs, recs = read_bam(bam_fn)
+    recs = list(recs)
+    kept = 0
+    for ctg, start, stop in (regions or [(None, 0, 1 << 62)]):
+        for r in recs:
+            if max_reads and kept >= max_reads:
+                return
+            if r["flag"] & (0x4 | 0x100 | 0x800) or r["ref_id"] < 0:
+                continue
+            rname = refs[r["ref_id"]][0]
+            ops, lens = r["cigar"] & 15, r["cigar"] >> 4
+            ref_span = int(lens[np.isin(ops, (0, 2, 3, 7, 8))].sum())
+            rstart, rstop = r["pos"], r["pos"] + ref_span
+            if ctg is not None and (rname != ctg or rstop <= start or rstart >= stop):
+                continue
+            # query_alignment_sequence / qualities: soft-clipped ends removed (hard clips are not in SEQ)
+            lead = int(lens[0]) if len(ops) and ops[0] == 4 else (int(lens[1]) if len(ops) > 1 and ops[0] == 5 and ops[1] == 4 else 0)
+            trail = int(lens[-1]) if len(ops) and ops[-1] == 4 else (int(lens[-2]) if len(ops) > 1 and ops[-1] == 5 and ops[-2] == 4 else 0)
+            seq = r["seq"][lead:len(r["seq"]) - trail]
+            quals = "*" if r["qual"] is None else "".join(chr(33 + int(x)) for x in r["qual"][lead:len(r["qual"]) - trail])
+            hp = r["tags"].get("HP")
+            kept += 1
+            yield (r["name"], r["flag"], rname, rstart, r["mapq"], _cigar_string(r["cigar"]), rstop, seq.upper(), quals,
+                   fa[rname][rstart:rstop].upper(), 0 if hp is None else int(hp))
+
+
+def create_header(outfile, refs, argv=None):
+    """bam.pyx:127-145: (re)creates the SAM with @HD / @SQ / @PG lines.  refs: [(name, length)]."""
+    if os.path.dirname(outfile):
+        os.makedirs(os.path.dirname(outfile), exist_ok=True)
+    with open(outfile, "w") as fh:
+        fh.write("@HD\tVN:1.6\tSO:coordinate\n")
+        for name, length in refs:
+            fh.write(f"@SQ\tSN:{name}\tLN:{length}\n")
+        fh.write(f"@PG\tID:realigner\tPN:realigner\tVN:{cfg.__version__}\tCL:{' '.join(argv if argv is not None else sys.argv)}\n")
+
+
+def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=None):
+    """realign.py:75-115 without pysam / Pool: header, ingest, GPU realignment, records appended in input order
+    (= coordinate order for a sorted BAM, which is what the header claims)."""
+    from .bam import realign_reads
+    if out_prefix is not None:
+        cfg.args.out_prefix = out_prefix
+    _, refs, _ = read_bam(bam_fn)
+    create_header(f"{cfg.args.out_prefix}.sam", refs, argv)
+    return realign_reads(get_read_data(bam_fn, fasta, regions, max_reads), write=True)
+
+
+# ------------------------------------------------------------------------------------------------ minimal BAM writer
+def _bgzf_block(payload: bytes) -> bytes:
+    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+    cdata = comp.compress(payload) + comp.flush()
+    bsize = len(cdata) + 25
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + cdata +
+            struct.pack("<II", zlib.crc32(payload) & 0xffffffff, len(payload)))
+
+
+def _reg2bin(beg, end):
+    end -= 1
+    for shift, off in ((14, 4681), (17, 585), (20, 73), (23, 9), (26, 1)):
+        if beg >> shift == end >> shift:
+            return off + (beg >> shift)
+    return 0
+
+
+def write_bam(path, header_text, refs, records):
+    """records: dicts with name, flag, ref_id, pos, mapq, cigar (list of (len, op_char)), seq, qual (bytes/None), tags
+    ({'HP': int} supported)."""
+    out = io.BytesIO()
+    text = header_text.encode()
+    out.write(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs)))
+    for name, length in refs:
+        out.write(struct.pack("<i", len(name) + 1) + name.encode() + b"\0" + struct.pack("<i", length))
+    for r in records:
+        cig = [(n << 4) | _OPS.index(op) for n, op in r["cigar"]]
+        seq = r["seq"]
+        codes = [_SEQ16.index(c) if c in _SEQ16 else 15 for c in seq] + [0]
+        packed = bytes((codes[i] << 4) | codes[i + 1] for i in range(0, len(seq), 2))
+        qual = bytes([0xFF] * len(seq)) if r.get("qual") is None else bytes(r["qual"])
+        tags = b"".join(b"HPi" + struct.pack("<i", v) if k == "HP" else b"" for k, v in r.get("tags", {}).items())
+        span = sum(n for n, op in r["cigar"] if op in "MDN=X") or 1
+        name = r["name"].encode() + b"\0"
+        body = struct.pack("<iiBBHHHiiii", r["ref_id"], r["pos"], len(name), r["mapq"], _reg2bin(r["pos"], r["pos"] + span),
+                           len(cig), r["flag"], len(seq), -1, -1, 0)
+        body += name + struct.pack(f"<{len(cig)}I", *cig) + packed + qual + tags
+        out.write(struct.pack("<i", len(body)) + body)
+    raw = out.getvalue()
+    with open(path, "wb") as fh:
+        for i in range(0, len(raw), 60000):
+            fh.write(_bgzf_block(raw[i:i + 60000]))
+        fh.write(_bgzf_block(b""))
