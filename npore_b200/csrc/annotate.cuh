@@ -41,7 +41,7 @@ struct AnnotateArgs {
     const uint8_t *ref_codes, *seq_codes;
     uint8_t *raw_ref, *raw_seq;    // 8 B per entry
     uint4 *colrec; uint2 *relaid; uint32_t *rowrec;
-    int max_n, max_l, nc, np_dim, np_clamp;
+    int max_n, max_l, nc, np_dim, np_clamp, inf_row;
 };
 
 // np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
@@ -131,7 +131,9 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         const int NC = a.nc;
         for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
             uint2 v = make_uint2(0u, 0u);
-            uint4 w = make_uint4(0u, 0u, 0u, 0u);
+            // "no candidate" SHR descriptor (NC <= 128): table row = the all-INF row, so the candidate can never win
+            const uint32_t empty = NC <= 128 ? ((uint32_t)a.inf_row << 10) : 0u;
+            uint4 w = make_uint4(empty, empty, 0u, 0u);
             if (j < len + 8) {
                 uint32_t lenm = 0, nshr = 0, nlen = 0;
 #pragma unroll
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                 uint32_t hasN = 0;
                 const uint32_t km = kmer2_of(s, len, j, hasN);
                 const bool more = nshr > 2 || nlen > 1;
-                if (more) { w.x = w.y = w.w = 0u; }
+                if (more) { w.x = w.y = empty; w.w = 0u; }
                 w.z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (km << 8);
             }
             out[j] = w;

@@ -179,7 +179,7 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(NPORE_ERR_CUDA);
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(NPORE_ERR_CUDA);
     ctx->P.r = r; ctx->P.W = 2 * r + 1; ctx->P.max_n = max_n; ctx->P.max_l = max_l; ctx->P.max_b_rows = max_b_rows;
-    ctx->P.np_dim = np_dim; ctx->P.np_clamp = max_l - 1;
+    ctx->P.np_dim = np_dim; ctx->P.np_clamp = max_l - 1; ctx->P.np_rows = np_n * np_dim;
     ctx->P.gap_open = indel_start; ctx->P.gap_ext = indel_extend;
     ctx->np_n = np_n;
     const int W = 2 * r + 1;
@@ -187,7 +187,7 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     ctx->tbs = np_tbs(ctx->cpl);
     if (ctx->d_sub.ensure(25 * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
     // score table re-laid with a guard column: np2[row][c] = np_scores[row][c-1], np2[row][0] = 100.0 (forward.cuh)
-    std::vector<float> np2((size_t)np_n * np_dim * (np_dim + 1));
+    std::vector<float> np2((size_t)(np_n * np_dim + 1) * (np_dim + 1), __builtin_inff());   // + one all-INF row: "no candidate"
     for (int64_t row = 0; row < (int64_t)np_n * np_dim; row++) {
         np2[(size_t)row * (np_dim + 1)] = 100.0f;
         memcpy(&np2[(size_t)row * (np_dim + 1) + 1], np_scores + row * np_dim, sizeof(float) * (size_t)np_dim);
@@ -418,6 +418,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         aa.raw_ref = ctx->d_raw_ref.as<uint8_t>(); aa.raw_seq = ctx->d_raw_seq.as<uint8_t>();
         aa.colrec = ctx->d_colrec.as<uint4>(); aa.relaid = ctx->d_relaid.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
         aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.np_dim = ctx->P.np_dim; aa.np_clamp = ctx->P.np_clamp;
+        aa.inf_row = ctx->np_n * ctx->P.np_dim;
         CU(cudaEventRecord(e0, ctx->stream));
         annotate_kernel<<<2 * sb.count, ANN_THREADS, 0, ctx->stream>>>(aa);
         CU(cudaGetLastError()); S.launches++;

@@ -67,6 +67,7 @@ struct OverflowRec { int32_t chunk, d, bc, run; };
 struct AlignParams {
     int r, W, max_n, max_l, max_b_rows;
     int np_dim, np_clamp;       // table side (101) and the index clamp max_l-1 (aln.pyx:269-272 as called at :615)
+    int np_rows;                // np_n * np_dim: index of the all-INF guard row of the re-laid table
     float gap_open, gap_ext;
 };
 

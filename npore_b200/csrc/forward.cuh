@@ -127,7 +127,8 @@ __device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, ui
     const uint32_t n = D & 7u, n4 = n << 2;
     const bool start = (D & ((uint32_t)NC << (TROW ? 20 : 19))) == 0u;  // array bit of the descriptor offset field
     const int run0 = start ? 0 : (int)(rr >> 16);
-    const bool ok = pred && (bc > (int)((sip >> n4) & 7u)) && (start || run0 > 0);
+    // (NC <= 128: an empty descriptor points at the all-INF table row and needs no predicate)
+    const bool ok = (TROW || pred) && (bc > (int)((sip >> n4) & 7u)) && (start || run0 > 0);
     const int L = (int)((D >> 3) & 0x7fu);
     uint32_t idx;
     if (TROW) {
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
     const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 20;      // rowrec "present" bits live at [20:25]
     const float *__restrict__ np = a.np_tab;          // re-laid table with guard column (api.cu)
     const int src_lane = (lane + 31) & 31;
+    const uint32_t empty_desc = NC <= 128 ? ((uint32_t)(a.P.np_rows) << 10) : 0u;      // annotate.cuh: "no candidate"
 
     for (;;) {
         int idx = 0;
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             bc[k] = (s + r) & (NC - 1);
             const int j0 = bc[k] - r;
             rw[k] = (j0 <= 0) ? row[-j0] : 0u;
-            cc[k] = (j0 > 0) ? col[j0] : (j0 == -r ? col[NC - r] : make_uint4(0u, 0u, 0u, 0u));
+            cc[k] = (j0 > 0) ? col[j0] : (j0 == -r ? col[NC - r] : make_uint4(empty_desc, empty_desc, 0u, 0u));
             if (j0 == 0) cc[k] = col[0];
         }
         int d0 = 0; uint32_t hist = 0; int Id = 0, Dd = 0;
@@ -348,12 +350,12 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             for (int k = 0; k < CPL; k++) {
                 in[k] = (unsigned)(bc[k] - lo) <= span && hi >= lo;
                 Sv[k] = infd; Lv[k] = infd; Sb[k] = 0.f; Lb[k] = 0.f; Sr[k] = 0; Lr[k] = 0;
-                p0[k] = in[k] && cc[k].x != 0u;
-                p1[k] = in[k] && cc[k].y != 0u;
+                p0[k] = in[k] && cc[k].x != empty_desc;          // (only consulted by the NC = 256 instantiation)
+                p1[k] = in[k] && cc[k].y != empty_desc;
                 pg[k] = in[k] && (cc[k].z & 1u);
                 const uint32_t lw = rw[k] & cc[k].w & nmask;               // one-hot LEN period vs "tract present" bits
                 pl[k] = in[k] && lw != 0u;
-                any1 |= cc[k].y; anyg |= cc[k].z; anyl |= lw;
+                any1 |= cc[k].y ^ empty_desc; anyg |= cc[k].z; anyl |= lw;
             }
             // ---- SHR gather: descriptor 0 (largest period; some lane almost always has one), then descriptor 1
 #pragma unroll
@@ -467,7 +469,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 Iv[k] = in[k] ? Iv[k] : edgev;
                 Dv[k] = in[k] ? Dv[k] : edgev;
                 Mr[k] = (in[k] && pk < (1u << NP_REC_TYP)) ? (int)pk : 0;
-                recs[k] = in[k] ? (pk | ((ieb >> 20) & NP_REC_IE) | ((deb >> 19) & NP_REC_DE)) : 0u;
+                recs[k] = in[k] ? (pk + (ieb >> 31) * NP_REC_IE + (deb >> 31) * NP_REC_DE) : 0u;   // IMADs: FMA pipe
             }
 
             // ---- history ring [ring][array][slot] + traceback row (slot order)
