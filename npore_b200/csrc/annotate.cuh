@@ -45,23 +45,70 @@ struct AnnotateArgs {
 };
 
 // np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
-// Per period n every position decides locally whether it heads a phase chain (fewer than n equalities e[] immediately
-// before it), finds the end of its run by walking forward, and walks its chain; chains of one period write disjoint
-// bytes, so one barrier per period suffices (the `longest` test reads the bytes of smaller periods).
+// Per period n: (1) the equality bits e[q] = (q+n < len && s[q]==s[q+n]) of every 32-position window go to shared
+// memory; (2) every position finds, with bit operations on those words, how many equalities immediately precede it
+// (fewer than n => it heads a phase chain) and where its run ends; (3) chain heads write their chain.  Chains of one
+// period write disjoint bytes, so two barriers per period suffice (the `longest` test reads bytes of smaller periods).
+#define ANN_MAX_WORDS 2048          // 65536 positions (max_b_rows <= 65000)
 __device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n, int max_l, uint8_t *raw, int32_t *full_out)
 {
-    const int tid = threadIdx.x;
+    __shared__ uint32_t s_e[ANN_MAX_WORDS + 2];
+    const int tid = threadIdx.x, lane = tid & 31;
     for (int q = tid; q < len; q += ANN_THREADS) reinterpret_cast<uint2 *>(raw)[q] = make_uint2(0u, 0u);
     if (full_out) for (int q = tid; q < len * 2 * max_n; q += ANN_THREADS) full_out[q] = 0;
+    const int nwords = (len + 31) >> 5;
     __syncthreads();
     for (int n = 1; n <= max_n; n++) {
+        for (int base = (tid >> 5) << 5; base < nwords * 32; base += ANN_THREADS) {
+            const int q = base + lane;
+            const bool e = (q + n < len) && (s[q] == s[q + n]);
+            const uint32_t bits = __ballot_sync(NP_FULL, e);
+            if (lane == 0) s_e[base >> 5] = bits;
+        }
+        if (tid == 0) s_e[nwords] = 0u;
+        __syncthreads();
         for (int h = tid; h < len; h += ANN_THREADS) {
-            int t = 0;                                        // equalities immediately before h
-            while (t < n && h - t - 1 >= 0 && h - t - 1 + n < len && s[h - t - 1] == s[h - t - 1 + n]) t++;
-            if (t == n) continue;                             // not among the first n positions of its run
-            int end = h;                                      // first position >= h with e[] false
-            while (end + n < len && s[end] == s[end + n]) end++;
+            const int w = h >> 5, b = h & 31;
+            const uint32_t cur = s_e[w];
+            // equalities immediately before h (only the first n matter)
+            const uint64_t below = (((uint64_t)cur << 32) | (uint64_t)(w ? s_e[w - 1] : 0u)) << (32 - b);     // bit 63 = e[h-1]
+            const int t = __clzll(~below | 1ull);
+            if (t >= n) continue;                             // not among the first n positions of its run
+            // first position >= h with e[] false
+            int end;
+            {
+                uint32_t inv = ~cur >> b;
+                if (b) inv &= (1u << (32 - b)) - 1u;
+                if (inv) end = h + __ffs(inv) - 1;
+                else {
+                    int ww = w + 1;
+                    while (s_e[ww] == 0xffffffffu) ww++;      // s_e[nwords] == 0 terminates
+                    end = (ww << 5) + __ffs(~s_e[ww]) - 1;
+                }
+            }
             if (end - h < 2 * n) continue;                    // fewer than 3 copies from the chain head on: nothing to write
+            // head of a chain with l >= 3: is the head itself an active writer (aln.pyx:237-243)?
+            const int l0 = (end - h) / n + 1;
+            bool act0 = s[h] != 0;
+            if (act0) {
+                const uint2 rw = reinterpret_cast<const uint2 *>(raw)[h];
+                for (int n2 = 1; n2 < n; n2++) {
+                    const uint32_t bb = ((n2 <= 4 ? rw.x >> (8 * (n2 - 1)) : rw.y >> (8 * (n2 - 5))) & 0x7fu);
+                    if (l0 * n <= (int)bb * n2) act0 = false;
+                }
+            }
+            if (act0 && l0 <= max_l) {
+                // common case: the head is the first writer and nothing is clamped -> L = l0, L_IDX = k for member k
+                for (int k = 0, p = h; k < l0; k++, p += n) {
+                    raw[(size_t)p * 8 + n - 1] = (uint8_t)(l0 | (k == 0 ? 0x80 : 0));
+                    if (full_out) {
+                        full_out[((size_t)p * 2 + 0) * max_n + n - 1] = l0;
+                        full_out[((size_t)p * 2 + 1) * max_n + n - 1] = k;
+                    }
+                }
+                continue;
+            }
+            // general walk: first active writer, last active writer with l > max_l (the clamp quirk)
             int first = -1, lfirst = 0, zlast = -1;
             for (int p = h; p <= end; p += n) {
                 const int m = end - p;
@@ -71,8 +118,8 @@ __device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n
                 if (act) {
                     const uint2 rw = reinterpret_cast<const uint2 *>(raw)[p];
                     for (int n2 = 1; n2 < n; n2++) {
-                        const uint32_t b = ((n2 <= 4 ? rw.x >> (8 * (n2 - 1)) : rw.y >> (8 * (n2 - 5))) & 0x7fu);
-                        if (l * n <= (int)b * n2) act = false;
+                        const uint32_t bb = ((n2 <= 4 ? rw.x >> (8 * (n2 - 1)) : rw.y >> (8 * (n2 - 5))) & 0x7fu);
+                        if (l * n <= (int)bb * n2) act = false;
                     }
                 }
                 if (act) {

@@ -519,6 +519,9 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     cudaEventElapsedTime(&S.ms_kernels_total, ctx->ev[2], e1);
     S.ms_annotate = ms_ann; S.ms_forward = ms_fwd; S.ms_traceback = ms_tb;
     S.n_sub_batches = (int)ctx->subs.size();
+#ifdef FWD_SPIN_DEBUG
+    { int sp = 0; cudaMemcpy(&sp, ctx->d_rr_ctl.as<int>() + 8, 4, cudaMemcpyDeviceToHost); S.n_sub_batches = sp; }
+#endif
     int ovf = 0;
     CU(cudaMemcpy(&ovf, ctx->d_ovf_count.p, 4, cudaMemcpyDeviceToHost));
     if (ovf > npore_ctx::OVF_CAP) return fail(ctx, NPORE_ERR_CAPACITY, "run-overflow list exhausted");

@@ -68,6 +68,9 @@ struct ForwardArgs {
 #ifndef FWD_RR
 #define FWD_RR 1
 #endif
+#ifndef FWD_SPIN_NS
+#define FWD_SPIN_NS 256
+#endif
 // words of saved per-lane state per cell: Mv1 Iv1 Dv1 dgv Mr1 dgr cc(4) rw
 #define FWD_RR_WORDS 11
 #define FWD_RR_HDR 32      // uint32 words: d, Id, Dd, hist
@@ -76,7 +79,7 @@ static __host__ __device__ inline size_t fwd_rr_state_words(int cpl) { return (s
 __global__ void rr_init_kernel(int *q, int cap, int n, int *ctl)
 {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) q[i] = i < n ? i : -1;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[0] = 0; ctl[1] = n; ctl[2] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl[0] = 0; ctl[1] = n; ctl[2] = 0; ctl[8] = 0; }
 }
 
 // #I among the last n ops (n = 1..6) for every 6-bit op history, packed 4 bits per n at nibble n
@@ -204,7 +207,10 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 int v;
                 while ((v = *qp) < 0) {
                     if (*(volatile int *)(a.rr_ctl + 2) >= a.n) { v = -2; break; }
-                    __nanosleep(256);
+#ifdef FWD_SPIN_DEBUG
+                    atomicAdd(a.rr_ctl + 8, 1);
+#endif
+                    __nanosleep(FWD_SPIN_NS);
                 }
                 if (v >= 0) *qp = -1;
                 idx = v;
