@@ -485,7 +485,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
             CU(cudaGetLastError()); S.launches++;
         } else CU(cudaMemsetAsync(ctx->d_rle_len.p, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
         if (flags & NPORE_OUT_STANDARDIZE) {
-            standardize_kernel<<<(n + FIN_THREADS - 1) / FIN_THREADS, FIN_THREADS, 0, ctx->stream>>>(fa);
+            standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa);
             CU(cudaGetLastError()); S.launches++;
             if (want_ops) {
                 expand_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);

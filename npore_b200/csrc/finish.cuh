@@ -6,7 +6,7 @@
 //                        push_indels_left(I, seq); push_inss_thru_dels (src/cig.pyx:102-192; the reference's `while True`
 //                        body runs exactly once because old_cig aliases int_cig); 'ID' -> 'M'.  Each pass is one
 //                        sequential sweep over the item's groups with a stack-like output (O(#groups), ~1000 per 10 kb
-//                        read, instead of the reference's 4 sweeps over every op), one thread per item.
+//                        read, instead of the reference's 4 sweeps over every op), one warp (lane 0) per item.
 //   expand_kernel        run-length words -> one char per op (the expanded 'MID' string realign_hap returns)
 //   scan / pack kernels  exclusive prefix of the per-item output sizes and a dense copy, so that the D2H transfer moves
 //                        exactly the bytes the caller gets.
@@ -165,10 +165,11 @@ __device__ __forceinline__ int rle_id_to_m(const uint32_t *in, int m, uint32_t *
     return st.m;
 }
 
+// one item per WARP, lane 0 does the sweeps: 32 different sequential sweeps inside one warp would serialise
 __global__ void __launch_bounds__(FIN_THREADS) standardize_kernel(const FinishArgs a)
 {
-    const int it = blockIdx.x * FIN_THREADS + threadIdx.x;
-    if (it >= a.n_items) return;
+    const int it = blockIdx.x * (FIN_THREADS / 32) + (threadIdx.x >> 5);
+    if (it >= a.n_items || (threadIdx.x & 31) != 0) return;
     const ItemDesc &I = a.items[it];
     uint32_t *A = a.rleA + I.out_off, *B = a.rleB + I.out_off;
     const uint8_t *ref = a.ref_codes + I.ref_start, *seq = a.seq_codes + I.seq_start;
