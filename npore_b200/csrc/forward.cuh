@@ -28,6 +28,7 @@
 // The algorithmic form (gather + carried BASE, relaid np-info) is validated on the CPU by oracle/pull_model.c.
 #pragma once
 #include "common.cuh"
+#include <type_traits>
 
 #ifndef FWD_WARPS
 #define FWD_WARPS 4
@@ -341,8 +342,12 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             const float edgev = infd + 100.f;
             const uint32_t dsh = (uint32_t)d * (uint32_t)(NC * 16);
             const bool steady = (unsigned)(Id - idLo) <= (unsigned)idSpan && (unsigned)(Dd - idLo) <= (unsigned)ddSpan && idSpan >= 0 && ddSpan >= 0;
+            // The cell body is instantiated twice: STEADY (every cell 1 <= b_col <= 2r-1 is interior with i,j >= 2: constant
+            // bounds, no first-row/column code) and generic (chunk head / tail).
+            auto cell_body = [&](auto steady_tag) {
+            constexpr bool STEADY = decltype(steady_tag)::value;
             int lo = 1, hi = 2 * r - 1;
-            if (!steady) {      // interior-cell bounds on b_col for this anti-diagonal (aln.pyx:497-507)
+            if (!STEADY) {      // interior-cell bounds on b_col for this anti-diagonal (aln.pyx:497-507)
                 lo = max(1, max(Id + r - imax, r - Dd)); hi = min(2 * r - 1, min(Id + r, jmax + r - Dd));
                 if (hi < lo) { lo = 1; hi = 0; }
             }
@@ -354,7 +359,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             uint32_t any1 = 0u, anyg = 0u, anyl = 0u;      // warp votes on plain ORs of the raw words (slightly conservative)
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
-                in[k] = (unsigned)(bc[k] - lo) <= span && hi >= lo;
+                in[k] = STEADY ? ((unsigned)(bc[k] - 1) <= (unsigned)(2 * r - 2)) : ((unsigned)(bc[k] - lo) <= span && hi >= lo);
                 Sv[k] = infd; Lv[k] = infd; Sb[k] = 0.f; Lb[k] = 0.f; Sr[k] = 0; Lr[k] = 0;
                 p0[k] = in[k] && cc[k].x != empty_desc;          // (only consulted by the NC = 256 instantiation)
                 p1[k] = in[k] && cc[k].y != empty_desc;
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 uint32_t deb = __float_as_uint(dv2 - dv1);                           // aln.pyx:558
                 uint32_t pk = (uint32_t)min(dgr[k] + 1, NP_RUN_SAT);                 // typ MAT = 0
                 float best = dgv[k] + lds_f(subbase + (rw[k] & 0xe0u) + (cc[k].z & 0x1cu));
-                if (!steady) {
+                if (!STEADY) {
                     const int i = Id + r - bc[k], j = Dd - r + bc[k];
                     if (i <= 1) ieb = 0u;                                            // aln.pyx:537-538 (run restarts), :525-528
                     if (j <= 1) deb = 0u;                                            // aln.pyx:559-560, :547-550
@@ -510,6 +515,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
                 dgv[k] = lMv[k]; dgr[k] = lMr[k];                 // next step's diagonal neighbour = this step's left
                 Mv1[k] = Mv[k]; Iv1[k] = Iv[k]; Dv1[k] = Dv[k]; Mr1[k] = Mr[k];
             }
+            };   // cell_body
+            if (steady) cell_body(std::true_type{}); else cell_body(std::false_type{});
         }
 #if FWD_RR
         if (dEnd < B) {     // slice over: save the chunk's state and hand it back to the run queue
