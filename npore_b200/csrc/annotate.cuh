@@ -179,7 +179,9 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
             uint2 v = make_uint2(0u, 0u);
             // "no candidate" SHR descriptor (NC <= 128): table row = the all-INF row, so the candidate can never win
-            const uint32_t empty = NC <= 128 ? ((uint32_t)a.inf_row << 10) : 0u;
+            // (its ring offset addresses the previous anti-diagonal's row, slot 0: a location nobody writes during the step)
+            const uint32_t empty_f = (uint32_t)((NP_RING - 1) * NC * 16) >> 2;
+            const uint32_t empty = NC <= 128 ? (((uint32_t)a.inf_row << 10) | (empty_f << 20)) : (empty_f << 19);
             uint4 w = make_uint4(empty, empty, 0u, 0u);
             if (j < len + 8) {
                 uint32_t lenm = 0, nshr = 0, nlen = 0;

@@ -317,6 +317,7 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
     CU(ctx->d_ops_off.ensure(sizeof(int64_t) * (size_t)(n + 1)));
     CU(ctx->d_rle_off.ensure(sizeof(int64_t) * (size_t)(n + 1)));
 
+    CU(cudaMemsetAsync(ctx->d_bits.p, 0, sizeof(uint32_t) * (size_t)(words + 128), ctx->stream));   // incl. the read-ahead padding
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (n) CU(cudaMemcpyAsync(ctx->d_items.p, ctx->items.data(), sizeof(ItemDesc) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (b->ref_total) CU(cudaMemcpyAsync(ctx->d_ref.p, b->ref_codes, (size_t)b->ref_total, cudaMemcpyHostToDevice, ctx->stream));

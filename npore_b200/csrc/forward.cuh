@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
     const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 20;      // rowrec "present" bits live at [20:25]
     const float *__restrict__ np = a.np_tab;          // re-laid table with guard column (api.cu)
     const int src_lane = (lane + 31) & 31;
-    const uint32_t empty_desc = NC <= 128 ? ((uint32_t)(a.P.np_rows) << 10) : 0u;      // annotate.cuh: "no candidate"
+    constexpr uint32_t empty_f = (uint32_t)((NP_RING - 1) * NC * 16) >> 2;
+    const uint32_t empty_desc = NC <= 128 ? (((uint32_t)(a.P.np_rows) << 10) | (empty_f << 20)) : (empty_f << 19);   // annotate.cuh: "no candidate"
 
     for (;;) {
         int idx = 0;
