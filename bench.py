@@ -28,7 +28,7 @@ sys.path.insert(0, ROOT)
 
 OPS_PER_CU = 28
 BYTES_PER_CU = 2         # packed (TYP,RUN) traceback record
-NCU_DRAM_BYTES_PER_LAUNCH = 8.255e9   # forward_kernel<2> on the C2 batch: 7.605 GB written + 0.650 GB read (ncu)
+NCU_DRAM_BYTES_PER_LAUNCH = 9.736e9   # forward_kernel<2> on the C2 batch: 8.867 GB written + 0.869 GB read (ncu, profiles/r01_final_*)
 
 
 def load_tables():
@@ -319,7 +319,7 @@ def main():
         "kernel_ms": {k: stats[k] for k in ("ms_plan", "ms_annotate", "ms_forward", "ms_traceback", "ms_finish", "ms_kernels_total")},
         "roofline": {"kernel": "forward_kernel<2>", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.reads, args.read_len) == (3000, 10000) else None,
-                     "traffic_source": "profiles/r01_v5_forward_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of this workload)",
+                     "traffic_source": "profiles/r01_final_forward_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of this workload)",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(n_cu * BYTES_PER_CU), "launch_ms": fwd * 1e3},
         "roofline_alu": {"bound": "cuda-core issue (SURVEY 8(d): 28 lane-ops per cell update)", "achieved": fwd_gcups,
