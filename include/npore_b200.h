@@ -131,6 +131,9 @@ int  npore_align_batch(npore_ctx *ctx, const npore_batch *batch, uint32_t flags,
 
 /* src/aln.pyx:179-251 on device: out is int32 [len][2][max_n] (L plane, L_IDX plane), like the reference's array */
 int  npore_get_np_info(npore_ctx *ctx, const uint8_t *codes, int32_t len, int32_t *out);
+/* the same for n_seqs sequences codes[off[i] .. off[i+1]) (off[0] == 0), one CTA each: src/bed.py:56-76 calls get_np_info
+ * once per chunk_width window of the reference; out is the concatenation of the per-sequence arrays */
+int  npore_get_np_info_batch(npore_ctx *ctx, int32_t n_seqs, const uint8_t *codes, const int64_t *off, int32_t *out);
 
 int  npore_last_stats(const npore_ctx *ctx, npore_stats *stats);
 const char *npore_strerror(int code);

@@ -39,7 +39,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_set_stream", "npore_count_chunks", "npore_upload", "npore_run", "npore_download",
-           "npore_align_batch", "npore_get_np_info", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
+           "npore_align_batch", "npore_get_np_info", "npore_get_np_info_batch", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
 
 _lib = None
 
@@ -63,6 +63,7 @@ def lib():
         L.npore_download.argtypes = [C.c_void_p, C.POINTER(Result)]
         L.npore_align_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_uint32, C.POINTER(Result)]
         L.npore_get_np_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.npore_get_np_info_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.npore_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.npore_strerror.argtypes = [C.c_int]
         L.npore_strerror.restype = C.c_char_p

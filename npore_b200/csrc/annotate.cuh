@@ -50,9 +50,11 @@ struct AnnotateArgs {
 // (fewer than n => it heads a phase chain) and where its run ends; (3) chain heads write their chain.  Chains of one
 // period write disjoint bytes, so two barriers per period suffice (the `longest` test reads bytes of smaller periods).
 #define ANN_MAX_WORDS 2048          // 65536 positions (max_b_rows <= 65000)
-__device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n, int max_l, uint8_t *raw, int32_t *full_out)
+__device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n, int max_l, uint8_t *raw, int32_t *full_out,
+                               uint32_t *ebits_long = nullptr)
 {
-    __shared__ uint32_t s_e[ANN_MAX_WORDS + 2];
+    __shared__ uint32_t s_e_smem[ANN_MAX_WORDS + 2];
+    uint32_t *s_e = ebits_long ? ebits_long : s_e_smem;         // long stand-alone sequences keep the words in global memory
     const int tid = threadIdx.x, lane = tid & 31;
     for (int q = tid; q < len; q += ANN_THREADS) reinterpret_cast<uint2 *>(raw)[q] = make_uint2(0u, 0u);
     if (full_out) for (int q = tid; q < len * 2 * max_n; q += ANN_THREADS) full_out[q] = 0;
@@ -245,7 +247,11 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
 
 // src/aln.pyx:179-251 as a stand-alone device entry (npore_get_np_info): one CTA, one sequence.
 __global__ void __launch_bounds__(ANN_THREADS)
-np_info_kernel(const uint8_t *s, int len, int max_n, int max_l, uint8_t *raw, int32_t *out)
+np_info_kernel(const uint8_t *codes, const int64_t *off, int max_n, int max_l, uint8_t *raw, int32_t *out, uint32_t *ebits)
 {
-    annotate_slice(s, len, max_n, max_l, raw, out);
+    // one CTA per sequence of the batch; sequences longer than the shared-memory window use global equality words
+    const int64_t b = off[blockIdx.x];
+    const int len = (int)(off[blockIdx.x + 1] - b);
+    annotate_slice(codes + b, len, max_n, max_l, raw + b * 8, out + b * 2 * max_n,
+                   len > ANN_MAX_WORDS * 32 ? ebits + (b >> 5) + 2 * blockIdx.x : nullptr);
 }

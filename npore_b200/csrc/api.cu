@@ -578,28 +578,45 @@ int npore_align_batch(npore_ctx *ctx, const npore_batch *batch, uint32_t flags, 
     return npore_download(ctx, result);
 }
 
-int npore_get_np_info(npore_ctx *ctx, const uint8_t *codes, int32_t len, int32_t *out)
+int npore_get_np_info_batch(npore_ctx *ctx, int32_t n_seqs, const uint8_t *codes, const int64_t *off, int32_t *out)
 {
-    if (!ctx || len < 0 || (len && (!codes || !out))) return NPORE_ERR_BAD_ARG;
-    if (len == 0) return NPORE_OK;
+    if (!ctx || n_seqs < 0 || (n_seqs && (!codes || !off || !out))) return NPORE_ERR_BAD_ARG;
+    if (n_seqs == 0) return NPORE_OK;
+    const int64_t total = off[n_seqs] - off[0];
+    if (off[0] != 0 || total < 0) return fail(ctx, NPORE_ERR_BAD_ARG, "offsets must start at 0 and increase");
+    for (int i = 0; i < n_seqs; i++)
+        if (off[i + 1] < off[i] || off[i + 1] - off[i] > 0x7ffffff0ll) return fail(ctx, NPORE_ERR_BAD_ARG, "bad sequence offsets");
+    if (total == 0) return NPORE_OK;
     CU(cudaSetDevice(ctx->device));
-    DevBuf d_s, d_raw, d_out;
-    const size_t ob = (size_t)len * 2 * ctx->P.max_n * sizeof(int32_t);
+    DevBuf d_s, d_off, d_raw, d_out, d_e;
+    const size_t ob = (size_t)total * 2 * ctx->P.max_n * sizeof(int32_t);
     int rc = NPORE_OK;
-    if (d_s.ensure(len) != cudaSuccess || d_raw.ensure((size_t)len * 8) != cudaSuccess || d_out.ensure(std::max<size_t>(ob, 4)) != cudaSuccess)
+    if (d_s.ensure((size_t)total) != cudaSuccess || d_off.ensure(sizeof(int64_t) * (size_t)(n_seqs + 1)) != cudaSuccess ||
+        d_raw.ensure((size_t)total * 8) != cudaSuccess || d_out.ensure(std::max<size_t>(ob, 4)) != cudaSuccess ||
+        d_e.ensure(sizeof(uint32_t) * (size_t)(total / 32 + 2 * (size_t)n_seqs + 8)) != cudaSuccess)
         rc = fail(ctx, NPORE_ERR_OOM, "np_info scratch");
     if (rc == NPORE_OK) {
-        cudaError_t e = cudaMemcpyAsync(d_s.p, codes, len, cudaMemcpyHostToDevice, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(d_s.p, codes, (size_t)total, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_off.p, off, sizeof(int64_t) * (size_t)(n_seqs + 1), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) {
-            np_info_kernel<<<1, ANN_THREADS, 0, ctx->stream>>>(d_s.as<uint8_t>(), len, ctx->P.max_n, ctx->P.max_l, d_raw.as<uint8_t>(), d_out.as<int32_t>());
+            np_info_kernel<<<n_seqs, ANN_THREADS, 0, ctx->stream>>>(d_s.as<uint8_t>(), d_off.as<int64_t>(), ctx->P.max_n, ctx->P.max_l,
+                                                                    d_raw.as<uint8_t>(), d_out.as<int32_t>(), d_e.as<uint32_t>());
             e = cudaGetLastError();
         }
         if (e == cudaSuccess && ob) e = cudaMemcpyAsync(out, d_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, NPORE_ERR_CUDA, "np_info", e);
     }
-    d_s.release(); d_raw.release(); d_out.release();
+    d_s.release(); d_off.release(); d_raw.release(); d_out.release(); d_e.release();
     return rc;
+}
+
+int npore_get_np_info(npore_ctx *ctx, const uint8_t *codes, int32_t len, int32_t *out)
+{
+    if (!ctx || len < 0 || (len && (!codes || !out))) return NPORE_ERR_BAD_ARG;
+    if (len == 0) return NPORE_OK;
+    const int64_t off[2] = {0, len};
+    return npore_get_np_info_batch(ctx, 1, codes, off, out);
 }
 
 int npore_last_stats(const npore_ctx *ctx, npore_stats *stats)

@@ -217,6 +217,18 @@ class Realigner:
         self._check(self._L.npore_get_np_info(self._ctx, codes.ctypes.data if len(codes) else None, len(codes), out.ctypes.data), "npore_get_np_info")
         return out[:len(codes)]
 
+    def get_np_info_batch(self, seqs):
+        """get_np_info for many code arrays in one launch (one CTA each); returns a list of int32 [len, 2, max_n]."""
+        seqs = [np.ascontiguousarray(s, dtype=np.uint8) for s in seqs]
+        off = np.zeros(len(seqs) + 1, dtype=np.int64)
+        np.cumsum([len(s) for s in seqs], out=off[1:])
+        if off[-1] == 0:
+            return [np.zeros((0, 2, self.params["max_n"]), np.int32) for _ in seqs]
+        codes = np.concatenate(seqs)
+        out = np.zeros((int(off[-1]), 2, self.params["max_n"]), dtype=np.int32)
+        self._check(self._L.npore_get_np_info_batch(self._ctx, len(seqs), codes.ctypes.data, off.ctypes.data, out.ctypes.data), "npore_get_np_info_batch")
+        return [out[off[i]:off[i + 1]] for i in range(len(seqs))]
+
     # convenience: python objects in, python objects out
     def align_many(self, refs, seqs, cigars, standardize=False, collapse=False):
         """refs/seqs: lists of uint8 code arrays; cigars: CIGAR texts (run-length or expanded).

@@ -311,3 +311,34 @@ def test_round_robin_time_slicing(tables, golden):
         for c, o, sc in zip(cases, outs, scores):
             assert o == c["out"] and np.array_equal(sc, np.array(c["scores"], np.float32))
         eng.close()
+
+
+def test_np_info_long_and_batched(tables, engine_factory):
+    """Stand-alone get_np_info on sequences longer than the chunk window (global equality words) and batched (N4)."""
+    eng = engine_factory()
+    rng = np.random.default_rng(17)
+    long_seq = synth.make_reference(150_000, rng, 0.4, "ACGTN")
+    long_seq = long_seq[:70_000] + "A" * 300 + long_seq[70_000:]
+    a = oracle.bases_to_int(long_seq)
+    assert np.array_equal(eng.get_np_info(a), oracle.get_np_info(a))
+    seqs = [oracle.bases_to_int(synth.make_reference(int(rng.integers(0, 5000)), rng, 0.5)) for _ in range(12)] + [np.zeros(0, np.uint8)]
+    for got, s_ in zip(eng.get_np_info_batch(seqs), seqs):
+        assert np.array_equal(got, oracle.get_np_info(s_))
+
+
+def test_np_region_beds(tables, tmp_path):
+    """bed.py:56-145 on the device np_info: regions = tract starts, padded, merged per n."""
+    from npore_b200 import bed, cfg
+    cfg.args.max_n, cfg.args.max_l = 6, 100
+    rng = np.random.default_rng(23)
+    refs = {"chr1": synth.make_reference(30_000, rng, 0.3), "chr2": synth.make_reference(8_000, rng, 0.6)}
+    windows = [("chr1", 0, 10_000), ("chr1", 10_000, 20_000), ("chr1", 20_000, 30_000), ("chr2", 0, 8_000)]
+    got = bed.get_np_regions_batch(windows, refs)
+    for (ctg, a, b), per_n in zip(windows, got):
+        info = oracle.get_np_info(oracle.bases_to_int(refs[ctg][a:b]))
+        for n in range(1, 7):
+            want = [(ctg, a + p, a + p + n * int(info[p, 0, n - 1])) for p in range(b - a) if info[p, 0, n - 1] and not info[p, 1, n - 1]]
+            assert per_n[n - 1] == want
+    assert bed.merge_regions([("c", 5, 9), ("c", 10, 12), ("c", 30, 31), ("b", 1, 2)], slop=1) == [("b", 0, 3), ("c", 4, 13), ("c", 29, 32)]
+    bed.save_np_region_beds(got, str(tmp_path / "np"))
+    assert (tmp_path / "np_1.bed").read_text().count("\n") > 0 and (tmp_path / "np_all.bed").exists()
