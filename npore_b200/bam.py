@@ -38,15 +38,13 @@ def realign_reads(read_data, write=True, max_batch_ops=64_000_000):
     fh = open(f"{cfg.args.out_prefix}.sam", "a") if write else None
     try:
         for batch in iter_batches(read_data, lambda rd: len(rd[9]) + len(rd[7]), max_batch_ops):
-            packed = PackedBatch([bases_to_int(rd[9]) for rd in batch], [bases_to_int(rd[7]) for rd in batch],
-                                 [cigar_to_rle(rd[5]) for rd in batch], pinned=False)
+            packed = PackedBatch.from_strings([rd[9] for rd in batch], [rd[7] for rd in batch], [rd[5] for rd in batch])
             res = eng.align_packed(packed, flags, eng.new_result(packed, flags, pinned=False))
             _report(res.status[:packed.n], "realign_read")
-            for k, rd in enumerate(batch):
-                line = sam_record(rd, res.cigar_text(k))
-                lines.append(line)
-                if fh:
-                    fh.write(line + "\n")
+            new = [sam_record(rd, cg) for rd, cg in zip(batch, res.cigar_texts())]
+            lines.extend(new)
+            if fh:
+                fh.write("\n".join(new) + "\n")
             with cfg.counter.get_lock():
                 cfg.counter.value += len(batch)
     finally:
@@ -67,8 +65,7 @@ def realign_haps(hap_data, max_batch_ops=300_000_000):
     eng = _engine(sub, npt, 5, 1, 20000, 30)
     out = []
     for batch in iter_batches(hap_data, lambda h: len(h[2]) + len(h[3]), max_batch_ops):
-        packed = PackedBatch([bases_to_int(h[3]) for h in batch], [bases_to_int(h[2]) for h in batch],
-                             [cigar_to_rle(h[4]) for h in batch], pinned=False)
+        packed = PackedBatch.from_strings([h[3] for h in batch], [h[2] for h in batch], [h[4] for h in batch])
         res = eng.align_packed(packed, NPORE_OUT_STANDARDIZE, eng.new_result(packed, NPORE_OUT_STANDARDIZE, pinned=False))
         _report(res.status[:packed.n], "realign_hap")
         for k, (contig, hap, seq, ref, _) in enumerate(batch):

@@ -20,6 +20,9 @@ for _k, _c in enumerate("MIDNSHP=XB"):            # cfg.py:27-32
 _OPCHAR = np.frombuffer(b"MIDNSHP=XB", dtype=np.uint8)
 
 
+_CODE_TABLE = bytes(({78: 0, 65: 1, 67: 2, 71: 3, 84: 4, 45: 5}).get(i, 0) for i in range(256))     # cig.pyx:212-229
+
+
 class NporeError(RuntimeError):
     pass
 
@@ -63,6 +66,71 @@ def rle_to_text(words: np.ndarray) -> str:
     return "".join(f"{n}{o}" for n, o in zip(lens, ops))
 
 
+def cigars_to_rle_batch(cigars):
+    """Many CIGAR texts -> (words uint32, off int64[n+1]) in one vectorised pass (no per-character Python).
+    All texts must be of one kind: run-length ('3=2D...') or expanded ('===DD...').  S/H groups are dropped."""
+    n = len(cigars)
+    off = np.zeros(n + 1, dtype=np.int64)
+    if n == 0:
+        return np.zeros(0, np.uint32), off
+    big = "\n".join(cigars).encode("latin-1") + b"\n"
+    a = np.frombuffer(big, dtype=np.uint8)
+    first = next((c for c in cigars if c), "")
+    if first[:1].isdigit():
+        isd = (a >= 48) & (a <= 57)
+        op_idx = np.flatnonzero(~isd)                          # op letters and the '\n' item separators
+        dpos = np.flatnonzero(isd)
+        gid = np.cumsum(~isd)[dpos]                            # group (next non-digit) of every digit
+        w = np.power(10, op_idx[gid] - dpos - 1, dtype=np.int64)
+        lens = np.bincount(gid, weights=(a[dpos] - 48).astype(np.int64) * w, minlength=len(op_idx)).astype(np.int64)
+        ops = _OPCODE[a[op_idx]]
+    else:
+        cut = np.flatnonzero((a[1:] != a[:-1]) | (a[1:] == 10)) + 1         # every separator is its own run
+        starts = np.concatenate(([0], cut))
+        lens = np.diff(np.concatenate((starts, [len(a)]))).astype(np.int64)
+        ops = _OPCODE[a[starts]]
+        op_idx = starts
+    sep = a[op_idx] == 10
+    item = np.cumsum(sep) - sep                                # item index of every group
+    keep = ~sep & (ops != 4) & (ops != 5)
+    if (ops[keep] == 255).any():
+        raise ValueError("unsupported CIGAR operation")
+    words = ((lens[keep] << 4) | ops[keep]).astype(np.uint32)
+    np.cumsum(np.bincount(item[keep], minlength=n)[:n], out=off[1:])
+    return words, off
+
+
+def rle_to_text_batch(words, off):
+    """Run-length words of many items -> list of CIGAR texts (collapse_cigar output), vectorised digit formatting."""
+    n = len(off) - 1
+    if n <= 0:
+        return []
+    words = np.asarray(words[:off[-1]], dtype=np.uint32)
+    lens = (words >> 4).astype(np.int64)
+    nd = np.ones(len(lens), dtype=np.int64)
+    for t in (10, 100, 1000, 10_000, 100_000, 1_000_000, 10_000_000, 100_000_000):
+        nd += lens >= t
+    width = nd + 1
+    end = np.cumsum(width)
+    pos = end - width
+    out = np.empty(int(end[-1]) if len(end) else 0, dtype=np.uint8)
+    for p in range(int(nd.max()) if len(nd) else 0):
+        m = nd > p
+        out[pos[m] + p] = 48 + (lens[m] // np.power(10, nd[m] - 1 - p)) % 10
+    out[pos + nd] = _OPCHAR[words & 15]
+    bstart = np.concatenate(([0], end))[np.asarray(off, dtype=np.int64)]
+    buf = out.tobytes()
+    return [buf[bstart[i]:bstart[i + 1]].decode("latin-1") for i in range(n)]
+
+
+def bases_to_int_batch(seqs):
+    """Many base strings -> (codes uint8 concatenated, lengths int32) with one table lookup (cig.pyx:212-229)."""
+    lens = np.fromiter((len(x) for x in seqs), dtype=np.int32, count=len(seqs))
+    joined = "".join(seqs).encode("latin-1")
+    codes = np.frombuffer(joined.translate(_CODE_TABLE), dtype=np.uint8) if joined else np.zeros(0, np.uint8)
+    return codes, lens
+
+
 class PackedBatch:
     """Flat host buffers in the layout of `npore_batch` (include/npore_b200.h)."""
 
@@ -103,6 +171,35 @@ class PackedBatch:
             np.concatenate(cigars, out=self.cigar_rle[:int(self.cigar_off[-1])])
         self.total_ops = int(self.ref_len.astype(np.int64).sum() + self.seq_len.astype(np.int64).sum())
 
+    @classmethod
+    def from_flat(cls, ref_codes, ref_len, seq_codes, seq_len, cigar_rle, cigar_off):
+        """Wrap already concatenated arrays (vectorised packers above) without copying item by item."""
+        self = cls.__new__(cls)
+        self.n = len(seq_len)
+        self.ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8) if len(ref_codes) else np.zeros(1, np.uint8)
+        self.seq_codes = np.ascontiguousarray(seq_codes, dtype=np.uint8) if len(seq_codes) else np.zeros(1, np.uint8)
+        self.ref_len = np.ascontiguousarray(ref_len, dtype=np.int32)
+        self.seq_len = np.ascontiguousarray(seq_len, dtype=np.int32)
+        self.ref_start = np.zeros(self.n, dtype=np.int64)
+        self.seq_start = np.zeros(self.n, dtype=np.int64)
+        if self.n:
+            np.cumsum(self.ref_len[:-1], out=self.ref_start[1:])
+            np.cumsum(self.seq_len[:-1], out=self.seq_start[1:])
+        self.ref_total = int(self.ref_len.astype(np.int64).sum())
+        self.seq_total = int(self.seq_len.astype(np.int64).sum())
+        self.cigar_off = np.ascontiguousarray(cigar_off, dtype=np.int64)
+        self.cigar_rle = np.ascontiguousarray(cigar_rle, dtype=np.uint32) if len(cigar_rle) else np.zeros(1, np.uint32)
+        self.total_ops = self.ref_total + self.seq_total
+        return self
+
+    @classmethod
+    def from_strings(cls, refs, seqs, cigars):
+        """refs / seqs: base strings; cigars: CIGAR texts (all run-length or all expanded)."""
+        rc, rl = bases_to_int_batch(refs)
+        sc, sl = bases_to_int_batch(seqs)
+        words, off = cigars_to_rle_batch(cigars)
+        return cls.from_flat(rc, rl, sc, sl, words, off)
+
     def c_struct(self):
         p = lambda a: a.ctypes.data  # noqa: E731
         return _lib.Batch(self.n, p(self.ref_codes), p(self.ref_start), p(self.ref_len), self.ref_total,
@@ -140,6 +237,10 @@ class BatchResult:
 
     def cigar_text(self, i) -> str:
         return rle_to_text(self.rle_words(i))
+
+    def cigar_texts(self):
+        """All collapsed CIGAR texts of the batch at once."""
+        return rle_to_text_batch(self.rle, self.rle_off)
 
     def scores(self, i) -> np.ndarray:
         return self.chunk_scores[self.score_off[i]:self.score_off[i + 1]]

@@ -143,3 +143,30 @@ def test_region_sharding_world_size_2(tmp_path):
                           "--master-port", "29541", str(script), ROOT], capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     assert "DIST_OK" in res.stdout
+
+
+def test_batch_codecs_match_single_item_codecs():
+    """The vectorised whole-batch packers / formatters used by realign_reads agree with the per-item functions."""
+    from npore_b200.engine import bases_to_int_batch, cigars_to_rle_batch, rle_to_text_batch
+    rng = np.random.default_rng(0)
+
+    def rnd():
+        k = int(rng.integers(0, 60))
+        return "".join(f"{int(rng.integers(1, 30000 if rng.random() < 0.05 else 40))}{'MIDSH=X'[int(rng.integers(0, 7))]}" for _ in range(k))
+    cigs = [rnd() for _ in range(300)] + ["", "5M", ""]
+    w, off = cigars_to_rle_batch(cigs)
+    assert all(np.array_equal(w[off[i]:off[i + 1]], cigar_to_rle(c)) for i, c in enumerate(cigs))
+    assert rle_to_text_batch(w, off) == [rle_to_text(cigar_to_rle(c)) for c in cigs]
+    ex = ["".join(rng.choice(list("=XIDM"), size=int(rng.integers(0, 300)))) for _ in range(100)] + ["", "I", "", ""]
+    w2, off2 = cigars_to_rle_batch(ex)
+    assert all(np.array_equal(w2[off2[i]:off2[i + 1]], cigar_to_rle(c)) for i, c in enumerate(ex))
+    codes, lens = bases_to_int_batch(["ACGTN-x", "", "GGGTTT"])
+    assert codes.tolist() == [1, 2, 3, 4, 0, 5, 0, 3, 3, 3, 4, 4, 4] and lens.tolist() == [7, 0, 6]
+    p = PackedBatch.from_strings(["ACG", "", "TT"], ["AC", "", "TTT"], ["2=1D", "", "2=1I"])
+    q = PackedBatch([cig.bases_to_int("ACG"), cig.bases_to_int(""), cig.bases_to_int("TT")],
+                    [cig.bases_to_int("AC"), cig.bases_to_int(""), cig.bases_to_int("TTT")],
+                    [cigar_to_rle("2=1D"), cigar_to_rle(""), cigar_to_rle("2=1I")], pinned=False)
+    for f in ("ref_start", "ref_len", "seq_start", "seq_len", "cigar_off"):
+        assert getattr(p, f).tolist() == getattr(q, f).tolist()
+    assert p.ref_codes[:p.ref_total].tolist() == q.ref_codes[:q.ref_total].tolist()
+    assert p.cigar_rle[:4].tolist() == q.cigar_rle[:4].tolist() and p.total_ops == q.total_ops
