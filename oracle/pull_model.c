@@ -10,8 +10,10 @@
  *   - per-position packed records: colrec (8 B, ref side) and rowrec (4 B, read side), "relaid" so that the
  *     record of column j holds what the SHR gather of cell (.,j) needs from columns j-1..j-6.
  * This file executes exactly that dataflow sequentially so it can be checked against oracle/npore_oracle.c
- * (and thereby the reference) on the CPU, before/independently of the CUDA transcription.  The kernels in
- * npore_b200/csrc/{annotate,forward,traceback}.cuh follow this file statement by statement.
+ * (and thereby the reference) on the CPU, before/independently of the CUDA transcription.  It pins the ALGORITHMIC
+ * form the kernels in npore_b200/csrc/{annotate,forward,traceback}.cuh use (gather + carried BASE, relaid np-info,
+ * chain-walker np_info, packed traceback record); the kernels' lane layout, descriptor encodings and scheduling have
+ * since moved on and are checked by the GPU parity tests.
  */
 #include <stdint.h>
 #include <stdlib.h>

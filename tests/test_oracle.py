@@ -97,3 +97,41 @@ def test_live_against_reference(tables):
         assert np.array_equal(gsc, np.array(wsc, dtype=np.float32))
         if len(ir):
             assert np.array_equal(np.asarray(ref.aln.get_np_info(ir)), oracle.get_np_info(ir))
+
+
+def test_pull_model_matches_oracle(tables):
+    """oracle/pull_model.c (the gather-form / carried-BASE / chain-walker dataflow the GPU kernels implement) against
+    the scatter-form oracle: op strings, bit-identical chunk scores, np_info."""
+    import ctypes as C
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(oracle.__file__))
+    subprocess.check_call(["make", "-C", here, "libpull_model.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(os.path.join(here, "libpull_model.so"))
+    u8 = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+    f32 = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+    L.pm_align.restype = C.c_int64
+    L.pm_align.argtypes = [u8, C.c_int, u8, C.c_int, C.c_char_p, C.c_int64, f32, f32, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                           C.c_int, C.c_int, C.c_char_p, C.c_int64, f32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pm_np_raw.argtypes = [u8, C.c_int, C.c_int, C.c_int, u8, np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")]
+    S, NP = tables
+    cm = synth.call_length_model(NP)
+    rng = np.random.default_rng(31)
+    pad = lambda a: a if a.size else np.zeros(1, np.uint8)  # noqa: E731
+    for _ in range(200):
+        rf, sq, cg, r, mb = synth.fuzz_case(rng, cm)
+        ir, iq = oracle.bases_to_int(rf), oracle.bases_to_int(sq)
+        want, wsc, wst = oracle.align(ir, iq, cg, S, NP, max_b_rows=mb, r=r, return_scores=True)
+        cap = len(ir) + len(iq) + 8
+        out = C.create_string_buffer(cap)
+        sc = np.zeros(cap // max(1, mb - 1) + 4, np.float32)
+        ns, st = C.c_int(0), C.c_int(0)
+        cb = cg.encode()
+        n = L.pm_align(pad(ir), len(ir), pad(iq), len(iq), cb, len(cb), S, NP, NP.shape[1], 6, 100, 5.0, 1.0, mb, r, out, cap, sc, len(sc),
+                       C.byref(ns), C.byref(st))
+        assert out.raw[:n].decode() == want and st.value == wst and np.array_equal(sc[:ns.value], wsc)
+        if len(ir):
+            raw = np.zeros((len(ir), 8), np.uint8); xs = np.zeros((len(ir), 8), np.int32)
+            L.pm_np_raw(ir, len(ir), 6, 100, raw, xs)
+            info = oracle.get_np_info(ir)
+            assert np.array_equal(raw[:, :6] & 0x7f, info[:, 0, :]) and np.array_equal(xs[:, :6], info[:, 1, :])
