@@ -342,3 +342,39 @@ def test_np_region_beds(tables, tmp_path):
     assert bed.merge_regions([("c", 5, 9), ("c", 10, 12), ("c", 30, 31), ("b", 1, 2)], slop=1) == [("b", 0, 3), ("c", 4, 13), ("c", 29, 32)]
     bed.save_np_region_beds(got, str(tmp_path / "np"))
     assert (tmp_path / "np_1.bed").read_text().count("\n") > 0 and (tmp_path / "np_all.bed").exists()
+
+
+def test_c_abi_error_behaviour(tables):
+    """include/npore_b200.h conventions: negative codes, never abort; call order upload -> run -> download."""
+    import ctypes as C
+    from npore_b200 import _lib
+    from npore_b200.engine import PackedBatch, Realigner, cigar_to_rle
+    S, NP = tables
+    L = _lib.lib()
+    ctx = C.c_void_p()
+    s32 = np.ascontiguousarray(S, np.float32); n32 = np.ascontiguousarray(NP, np.float32)
+    bad_args = [dict(max_n=7), dict(max_l=128), dict(max_b_rows=1), dict(r=0), dict(r=200), dict(device=99)]
+    for kw in bad_args:
+        a = dict(device=0, max_n=6, max_l=100, max_b_rows=20000, r=30); a.update(kw)
+        rc = L.npore_ctx_create(C.byref(ctx), a["device"], s32.ctypes.data, n32.ctypes.data, 6, 101, a["max_n"], a["max_l"], 5.0, 1.0, a["max_b_rows"], a["r"])
+        assert rc == -1 and not ctx.value, kw                                   # NPORE_ERR_BAD_ARG, no context leaked
+    assert L.npore_strerror(-5).startswith(b"call out of order")
+    eng = Realigner(S, NP)
+    packed = PackedBatch([oracle.bases_to_int("ACGTACGT")], [oracle.bases_to_int("ACGTACGT")], [cigar_to_rle("8=")], pinned=False)
+    res = eng.new_result(packed, 0, pinned=False)
+    r = res.c_struct()
+    assert L.npore_run(eng._ctx, 0) == -5                                       # run before upload
+    assert L.npore_download(eng._ctx, C.byref(r)) == -5                         # download before run
+    eng.upload(packed)
+    assert L.npore_download(eng._ctx, C.byref(r)) == -5
+    assert L.npore_run(eng._ctx, 4) == -1                                       # NO_EXPANDED without RLE
+    eng.run(0)
+    r.ops_capacity = 3                                                          # caller buffer too small
+    assert L.npore_download(eng._ctx, C.byref(r)) == -6 and b"too small" in L.npore_last_error(eng._ctx)
+    r = res.c_struct()
+    assert L.npore_download(eng._ctx, C.byref(r)) == 0 and res.ops_str(0) == "=" * 8
+    # out-of-range sequence window
+    packed.ref_len[0] = 100
+    b = packed.c_struct()
+    assert L.npore_upload(eng._ctx, C.byref(b)) == -1
+    eng.close()
