@@ -19,6 +19,10 @@
  *                            exactly upload + run + download.
  *   npore_get_np_info     <- src/aln.pyx:179-251 get_np_info() (device implementation, for tests and
  *                            for callers such as src/bed.py:56-76).
+ *   npore_confusion_batch <- src/bam.pyx:351-510 calc_confusion_matrices() for a batch of get_ranges() windows
+ *                            (src/bam.pyx:149-164), computed from the alignments themselves instead of the text of
+ *                            `samtools mpileup | cut -f5` (src/bam.pyx:300-314); the sum over the ranges is what
+ *                            src/bam.pyx:184-192 get_confusion_matrices() reduces to.
  *   npore_last_stats      <- the wall-clock prints of src/realign.py:109,115 (per-phase device times,
  *                            cell-update counts).
  *
@@ -134,6 +138,30 @@ int  npore_get_np_info(npore_ctx *ctx, const uint8_t *codes, int32_t len, int32_
 /* the same for n_seqs sequences codes[off[i] .. off[i+1]) (off[0] == 0), one CTA each: src/bed.py:56-76 calls get_np_info
  * once per chunk_width window of the reference; out is the concatenation of the per-sequence arrays */
 int  npore_get_np_info_batch(npore_ctx *ctx, int32_t n_seqs, const uint8_t *codes, const int64_t *off, int32_t *out);
+
+/* Basecaller confusion matrices (src/bam.pyx:351-510).  One range = one (ctg, start, end) tuple of get_ranges().
+ * The caller has already dropped the reads samtools mpileup drops by default (flag & (UNMAP|SECONDARY|QCFAIL|DUP));
+ * reads are alignments as stored in the BAM (soft clips included in seq and CIGAR), coordinate sorted. */
+typedef struct npore_pileup_batch {
+    int32_t        n_ranges;
+    const int64_t *range_start;      /* [R] 0-based, contig coordinates                                          */
+    const int64_t *range_end;        /* [R] half-open                                                            */
+    const uint8_t *ref_ascii;        /* raw contig bytes, range r owns [ref_off[r], ref_off[r+1]) =              */
+    const int64_t *ref_off;          /* [R+1]  contig[start : min(contig_len, end + 1 + max_n)]                  */
+    int32_t        n_reads;
+    const int64_t *read_pos;         /* [n] 0-based leftmost reference position                                  */
+    const uint8_t *seq_ascii;        /* concatenated read bases (ASCII, any case)                                */
+    const uint8_t *qual;             /* concatenated base qualities (phred, not +33), same offsets; NULL = all pass */
+    const int64_t *seq_off;          /* [n+1]                                                                    */
+    const uint32_t *cigar_rle;       /* concatenated BAM words len<<4|op, op in M I D N S H = X (P, B: error)    */
+    const int64_t *cigar_off;        /* [n+1]                                                                    */
+    const int32_t *range_reads;      /* per range: indices of the reads overlapping it, ascending position       */
+    const int64_t *range_reads_off;  /* [R+1]                                                                    */
+    int32_t        min_base_q;       /* samtools mpileup -Q (default 13)                                         */
+} npore_pileup_batch;
+/* outputs (int64, overwritten with the totals of this call): subs[5][5] indexed [ref][call], nps[max_n][max_l+1][max_l+1]
+ * indexed [n-1][ref copies][called copies], inss[max_l+1], dels[max_l+1] */
+int  npore_confusion_batch(npore_ctx *ctx, const npore_pileup_batch *batch, int64_t *subs, int64_t *nps, int64_t *inss, int64_t *dels);
 
 int  npore_last_stats(const npore_ctx *ctx, npore_stats *stats);
 const char *npore_strerror(int code);

@@ -38,8 +38,16 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class PileupBatch(C.Structure):
+    _fields_ = [("n_ranges", C.c_int32), ("range_start", C.c_void_p), ("range_end", C.c_void_p),
+                ("ref_ascii", C.c_void_p), ("ref_off", C.c_void_p),
+                ("n_reads", C.c_int32), ("read_pos", C.c_void_p), ("seq_ascii", C.c_void_p), ("qual", C.c_void_p),
+                ("seq_off", C.c_void_p), ("cigar_rle", C.c_void_p), ("cigar_off", C.c_void_p),
+                ("range_reads", C.c_void_p), ("range_reads_off", C.c_void_p), ("min_base_q", C.c_int32)]
+
+
 EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_set_stream", "npore_count_chunks", "npore_upload", "npore_run", "npore_download",
-           "npore_align_batch", "npore_get_np_info", "npore_get_np_info_batch", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
+           "npore_align_batch", "npore_get_np_info", "npore_get_np_info_batch", "npore_confusion_batch", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
 
 _lib = None
 
@@ -64,6 +72,7 @@ def lib():
         L.npore_align_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.c_uint32, C.POINTER(Result)]
         L.npore_get_np_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.npore_get_np_info_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.npore_confusion_batch.argtypes = [C.c_void_p, C.POINTER(PileupBatch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.npore_last_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.npore_strerror.argtypes = [C.c_int]
         L.npore_strerror.restype = C.c_char_p

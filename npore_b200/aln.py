@@ -6,9 +6,11 @@
   get_np_info(seq) -> int32 [len, 2, max_n]                 aln.pyx:179-251
   dump(ref, seq, cigar)                                     aln.pyx:791-...   (pretty printer, host)
 
-Like the reference, max_n / max_l are read from cfg.args at call time.  Score-table construction
-(calc_score_matrices, aln.pyx:62-96) is deliberately not re-implemented: its outputs are opaque inputs
-of this path -- build them with the reference and pass the arrays in.
+  calc_score_matrices(subs, nps, inss, dels, eps=0.01)     aln.pyx:62-96     (table construction, host, one-off)
+  fix_matrix_properties(scores, delta=0.01)                 aln.pyx:11-58
+
+Like the reference, max_n / max_l are read from cfg.args at call time.  The two table builders run once per
+basecaller model on 60k numbers; they are host numpy and not part of the GPU path.
 """
 import numpy as np
 
@@ -99,6 +101,64 @@ def dump(ref, seq, cigar):
         print("REF: " + "".join(ref_str[k:k + 80]))
         print("     " + "".join(cig_str[k:k + 80]))
         print("SEQ: " + "".join(seq_str[k:k + 80]) + "\n")
+
+
+def fix_matrix_properties(scores, delta=0.01):
+    """aln.pyx:11-58.  In place, per period n, on the (ref_len, call_len) plane:
+      1. rows 0..2 (no such tract) cost 20 for every call length >= 1; a correct call (the diagonal) costs 0;
+      2. above the diagonal (insertions) a cell is at least delta worse than the cell below it and the cell to its left;
+      3. below the diagonal, rows >= 4 (deletions): at least delta worse than the cell to its right and the cell above;
+      4. rows >= 4: an off-diagonal cell is at least delta better than its upper-left neighbour (same INDEL, shorter tract).
+    Sweeps 2-4 are recurrences evaluated in the reference's order with the array's own scalar type, so the result is
+    the reference's to the bit."""
+    size = scores.shape[1]
+    for plane in scores:
+        plane[0:3, 1:] = 20
+        idx = np.arange(1, size)
+        plane[idx, idx] = 0
+        for col in range(1, size):
+            for row in range(col - 1, -1, -1):
+                plane[row, col] = max(plane[row, col], plane[row + 1, col] + delta, plane[row, col - 1] + delta)
+        for row in range(4, size):
+            for col in range(row - 1, -1, -1):
+                plane[row, col] = max(plane[row, col], plane[row, col + 1] + delta, plane[row - 1, col] + delta)
+        for row in range(4, size):
+            for col in range(1, size):
+                if row != col:
+                    plane[row, col] = min(plane[row, col], plane[row - 1, col - 1] - delta)
+    return scores
+
+
+def _neg_log_frac(counts, totals, eps):
+    return -np.log((np.asarray(counts, dtype=np.float64) + eps) / (np.asarray(totals, dtype=np.float64) + eps))
+
+
+def calc_score_matrices(subs, nps, inss, dels, eps=0.01):
+    """aln.pyx:62-96: confusion-matrix counts -> (sub_scores, np_scores, ins_scores, del_scores), all float32.
+    score = -ln((count + eps) / (row total + eps)); only indices < max_l are filled (the last row / column of every
+    table stays 0 before fix_matrix_properties, as in the reference); sub_scores row/column 0 (N) and diagonal are 0."""
+    max_n, max_l = int(cfg.args.max_n), int(cfg.args.max_l)
+    nps = np.asarray(nps)
+    np_scores = np.zeros(nps.shape, dtype=np.float32)
+    np_scores[:max_n, :max_l, :max_l] = _neg_log_frac(nps[:max_n, :max_l, :max_l], nps[:max_n, :max_l].sum(axis=2)[:, :, None], eps)
+    np_scores = fix_matrix_properties(np_scores)
+
+    subs = np.asarray(subs)
+    sub_scores = np.zeros((cfg.nbases, cfg.nbases), dtype=np.float32)
+    sub_scores[1:, 1:] = _neg_log_frac(subs[1:cfg.nbases, 1:cfg.nbases], subs[1:cfg.nbases].sum(axis=1)[:, None], eps)
+    sub_scores[np.arange(cfg.nbases), np.arange(cfg.nbases)] = 0
+
+    inss, dels = np.asarray(inss), np.asarray(dels)
+    ins_scores = np.zeros(inss.shape, dtype=np.float32)
+    ins_scores[:max_l] = _neg_log_frac(inss[:max_l], inss.sum(), eps)
+    del_scores = np.zeros(dels.shape, dtype=np.float32)
+    del_scores[:max_l] = _neg_log_frac(dels[:max_l], dels.sum(), eps)
+    return sub_scores, np_scores, ins_scores, del_scores
+
+
+def plot_np_score_matrices(nps, max_l=50):
+    """aln.pyx:100-175 draws PNGs with matplotlib; plotting is outside this package's scope."""
+    raise NotImplementedError("plotting is not part of npore_b200; use the reference's plot_np_score_matrices on the same arrays")
 
 
 def load_score_tables(path):

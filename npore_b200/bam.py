@@ -14,6 +14,7 @@ from .aln import _engine, _report
 from .cig import bases_to_int
 from .engine import (NPORE_OUT_NO_EXPANDED, NPORE_OUT_RLE, NPORE_OUT_STANDARDIZE, PackedBatch, cigar_to_rle)
 from .scheduler import iter_batches
+from .confusion import calc_confusion_matrices, calc_confusion_matrices_batch, get_confusion_matrices, get_ranges  # noqa: F401  (bam.pyx:149-205, 351-510)
 
 
 def sam_record(read_data, cigar_text):

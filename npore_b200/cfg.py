@@ -6,7 +6,8 @@ from collections import defaultdict
 
 # globals read by the hot path at call time (aln.pyx:207-208, 436-437): max_n, max_l; tables live on
 # args.sub_scores / args.np_scores (realign.py:92-93); out_prefix names the SAM (bam.pyx:82) and the log (aln.pyx:691)
-args = argparse.Namespace(max_n=6, max_l=100, out_prefix="npore_out", sub_scores=None, np_scores=None, device=0)
+args = argparse.Namespace(max_n=6, max_l=100, out_prefix="npore_out", sub_scores=None, np_scores=None, device=0,
+                          chunk_width=100000, stats_dir="stats", recalc_cms=False, refs=None, bam=None, regions=None)
 
 
 class _Counter:

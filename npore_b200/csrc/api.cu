@@ -25,6 +25,7 @@
 #include "forward.cuh"
 #include "traceback.cuh"
 #include "finish.cuh"
+#include "confusion.cuh"
 
 namespace {
 
@@ -75,6 +76,7 @@ struct npore_ctx {
     // per sub-batch scratch
     DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_tb, d_rr_q, d_rr_ctl, d_rr_state;
     int rr_slice = 512;
+    DevBuf d_cm[22];                     // npore_confusion_batch staging (kept between calls)
     HostBuf h_small;
     int64_t pack_ops_total = 0, pack_rle_total = 0;
     std::vector<ItemDesc> items;
@@ -218,6 +220,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
                       &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
                       &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
     for (auto *b : bufs) b->release();
+    for (auto &b : ctx->d_cm) b.release();
     ctx->h_small.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->sub_ev) cudaEventDestroy(e);
@@ -617,6 +620,120 @@ int npore_get_np_info(npore_ctx *ctx, const uint8_t *codes, int32_t len, int32_t
     if (len == 0) return NPORE_OK;
     const int64_t off[2] = {0, len};
     return npore_get_np_info_batch(ctx, 1, codes, off, out);
+}
+
+int npore_confusion_batch(npore_ctx *ctx, const npore_pileup_batch *b, int64_t *subs, int64_t *nps, int64_t *inss, int64_t *dels)
+{
+    if (!ctx || !b || !subs || !nps || !inss || !dels || b->n_ranges < 0 || b->n_reads < 0) return NPORE_ERR_BAD_ARG;
+    const int R = b->n_ranges, n = b->n_reads, T = ctx->P.max_l + 1;
+    const size_t n_out = 25 + (size_t)ctx->P.max_n * T * T + 2 * (size_t)T;
+    std::memset(subs, 0, 25 * sizeof(int64_t)); std::memset(nps, 0, (size_t)ctx->P.max_n * T * T * sizeof(int64_t));
+    std::memset(inss, 0, T * sizeof(int64_t)); std::memset(dels, 0, T * sizeof(int64_t));
+    if (R == 0) return NPORE_OK;
+    if (!b->range_start || !b->range_end || !b->ref_ascii || !b->ref_off || !b->range_reads_off ||
+        (n && (!b->read_pos || !b->seq_ascii || !b->seq_off || !b->cigar_rle || !b->cigar_off)))
+        return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: null array");
+    if (b->ref_off[0] != 0 || b->range_reads_off[0] != 0 || (n && (b->seq_off[0] != 0 || b->cigar_off[0] != 0)))
+        return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: offsets must start at 0");
+    std::vector<int64_t> pos_off((size_t)R + 1, 0);
+    for (int r = 0; r < R; r++) {
+        const int64_t len = b->range_end[r] - b->range_start[r], have = b->ref_off[r + 1] - b->ref_off[r];
+        if (len <= 0 || len > 0x7ffffff0ll || b->range_start[r] < 0 || have < len || have > 0x7ffffff0ll ||
+            b->range_reads_off[r + 1] < b->range_reads_off[r])
+            return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: bad range (need end > start and the reference bytes of the whole range)");
+        pos_off[r + 1] = pos_off[r] + len;
+    }
+    const int64_t n_list = b->range_reads_off[R], total_pos = pos_off[R], total_ref = b->ref_off[R];
+    if (n_list && !b->range_reads) return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: null read list");
+    for (int r = 0; r < R; r++)
+        for (int64_t k = b->range_reads_off[r]; k < b->range_reads_off[r + 1]; k++) {
+            const int32_t rd = b->range_reads[k];
+            if (rd < 0 || rd >= n) return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: read index out of range");
+            if (k > b->range_reads_off[r] && b->read_pos[rd] < b->read_pos[b->range_reads[k - 1]])
+                return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: a range's reads must be in coordinate order");
+        }
+    for (int i = 0; i < n; i++)
+        if (b->seq_off[i + 1] < b->seq_off[i] || b->cigar_off[i + 1] < b->cigar_off[i] || b->seq_off[i + 1] - b->seq_off[i] > 0x7ffffff0ll)
+            return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: bad read offsets");
+    const int64_t seq_total = n ? b->seq_off[n] : 0, n_words = n ? b->cigar_off[n] : 0;
+    CU(cudaSetDevice(ctx->device));
+    DevBuf *d = ctx->d_cm;
+    auto put = [&](int slot, const void *src, size_t bytes) -> cudaError_t {
+        cudaError_t e = d[slot].ensure(std::max<size_t>(bytes, 16));
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(d[slot].p, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        return e;
+    };
+    auto zero = [&](int slot, size_t bytes) -> cudaError_t {
+        cudaError_t e = d[slot].ensure(std::max<size_t>(bytes, 16));
+        if (e == cudaSuccess) e = cudaMemsetAsync(d[slot].p, 0, std::max<size_t>(bytes, 16), ctx->stream);
+        return e;
+    };
+    cudaError_t e = cudaSuccess;
+    int rc = NPORE_OK;
+    const bool have_q = b->qual != nullptr;
+#define CM_TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+    CM_TRY(put(0, b->range_start, sizeof(int64_t) * R));
+    CM_TRY(put(1, b->range_end, sizeof(int64_t) * R));
+    CM_TRY(put(2, b->ref_ascii, (size_t)total_ref));
+    CM_TRY(put(3, b->ref_off, sizeof(int64_t) * (R + 1)));
+    CM_TRY(d[4].ensure(std::max<size_t>((size_t)total_ref, 16)));                       // codes
+    CM_TRY(d[5].ensure(std::max<size_t>((size_t)total_ref * 8, 16)));                   // raw np_info
+    CM_TRY(d[6].ensure(sizeof(uint32_t) * (size_t)(total_ref / 32 + 2 * (size_t)R + 8)));   // equality words
+    CM_TRY(put(7, b->read_pos, sizeof(int64_t) * n));
+    CM_TRY(put(8, b->seq_ascii, (size_t)seq_total));
+    if (have_q) CM_TRY(put(9, b->qual, (size_t)seq_total));
+    CM_TRY(put(10, b->seq_off, sizeof(int64_t) * (n + 1)));
+    CM_TRY(put(11, b->cigar_rle, sizeof(uint32_t) * (size_t)n_words));
+    CM_TRY(put(12, b->cigar_off, sizeof(int64_t) * (n + 1)));
+    CM_TRY(d[13].ensure(std::max<size_t>(sizeof(int32_t) * (size_t)n_words, 16)));
+    CM_TRY(d[14].ensure(std::max<size_t>(sizeof(int32_t) * (size_t)n_words, 16)));
+    CM_TRY(d[15].ensure(std::max<size_t>(sizeof(int64_t) * (size_t)n, 16)));
+    CM_TRY(put(16, b->range_reads, sizeof(int32_t) * (size_t)n_list));
+    CM_TRY(put(17, b->range_reads_off, sizeof(int64_t) * (R + 1)));
+    CM_TRY(d[18].ensure(std::max<size_t>(sizeof(int64_t) * (size_t)n_list, 16)));
+    CM_TRY(d[19].ensure(std::max<size_t>(sizeof(int32_t) * (size_t)total_pos, 16)));
+    CM_TRY(put(20, pos_off.data(), sizeof(int64_t) * (R + 1)));
+    CM_TRY(zero(21, sizeof(int32_t) * (size_t)(total_pos + R) + sizeof(unsigned long long) * n_out + 16));
+    if (e != cudaSuccess) rc = fail(ctx, e == cudaErrorMemoryAllocation ? NPORE_ERR_OOM : NPORE_ERR_CUDA, "confusion staging", e);
+    std::vector<unsigned long long> h_out(n_out + 2);
+    if (rc == NPORE_OK) {
+        ConfusionArgs a;
+        a.n_ranges = R; a.n_reads = n;
+        a.range_start = d[0].as<int64_t>(); a.range_end = d[1].as<int64_t>();
+        a.ref_ascii = d[2].as<uint8_t>(); a.ref_off = d[3].as<int64_t>(); a.ref_codes = d[4].as<uint8_t>();
+        a.raw = d[5].as<uint8_t>(); a.ebits = d[6].as<uint32_t>();
+        a.read_pos = d[7].as<int64_t>(); a.seq = d[8].as<uint8_t>(); a.qual = have_q ? d[9].as<uint8_t>() : nullptr;
+        a.seq_off = d[10].as<int64_t>(); a.rle = d[11].as<uint32_t>(); a.cig_off = d[12].as<int64_t>();
+        a.g_roff = d[13].as<int32_t>(); a.g_qoff = d[14].as<int32_t>(); a.read_end = d[15].as<int64_t>();
+        a.range_reads = d[16].as<int32_t>(); a.range_reads_off = d[17].as<int64_t>(); a.list_maxend = d[18].as<int64_t>();
+        a.line_of = d[19].as<int32_t>(); a.pos_off = d[20].as<int64_t>();
+        // zeroed block: outputs first (8-byte aligned), then the coverage difference array
+        unsigned long long *o = d[21].as<unsigned long long>();
+        a.subs = o; a.nps = o + 25; a.inss = a.nps + (size_t)ctx->P.max_n * T * T; a.dels = a.inss + T;
+        a.bad = reinterpret_cast<int *>(o + n_out);
+        a.diff = reinterpret_cast<int32_t *>(o + n_out + 2);
+        a.max_n = ctx->P.max_n; a.max_l = ctx->P.max_l; a.min_bq = b->min_base_q;
+        const int sm = ctx->stats.sm_count > 0 ? ctx->stats.sm_count : 148;
+        cm_codes_kernel<<<sm * 4, 256, 0, ctx->stream>>>(a.ref_ascii, a.ref_codes, total_ref);
+        cm_np_kernel<<<R, ANN_THREADS, 0, ctx->stream>>>(a);
+        if (n) cm_read_kernel<<<(n + CM_THREADS / 32 - 1) / (CM_THREADS / 32), CM_THREADS, 0, ctx->stream>>>(a);
+        cm_range_kernel<<<R, CM_THREADS, 0, ctx->stream>>>(a);
+        const int64_t want = (total_pos + CM_THREADS / 32 - 1) / (CM_THREADS / 32);
+        cm_pileup_kernel<<<(int)std::min<int64_t>(want, (int64_t)sm * 8), CM_THREADS, 0, ctx->stream>>>(a);
+        e = cudaGetLastError();
+        CM_TRY(cudaMemcpyAsync(h_out.data(), o, sizeof(unsigned long long) * (n_out + 2), cudaMemcpyDeviceToHost, ctx->stream));
+        CM_TRY(cudaStreamSynchronize(ctx->stream));
+        if (e != cudaSuccess) rc = fail(ctx, NPORE_ERR_CUDA, "confusion kernels", e);
+    }
+#undef CM_TRY
+
+    if (rc != NPORE_OK) return rc;
+    if (*reinterpret_cast<int *>(&h_out[n_out])) return fail(ctx, NPORE_ERR_BAD_ARG, "confusion: CIGAR op P or B is not supported");
+    std::memcpy(subs, h_out.data(), 25 * sizeof(int64_t));
+    std::memcpy(nps, h_out.data() + 25, (size_t)ctx->P.max_n * T * T * sizeof(int64_t));
+    std::memcpy(inss, h_out.data() + 25 + (size_t)ctx->P.max_n * T * T, T * sizeof(int64_t));
+    std::memcpy(dels, h_out.data() + 25 + (size_t)ctx->P.max_n * T * T + T, T * sizeof(int64_t));
+    return NPORE_OK;
 }
 
 int npore_last_stats(const npore_ctx *ctx, npore_stats *stats)

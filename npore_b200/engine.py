@@ -330,6 +330,22 @@ class Realigner:
         self._check(self._L.npore_get_np_info_batch(self._ctx, len(seqs), codes.ctypes.data, off.ctypes.data, out.ctypes.data), "npore_get_np_info_batch")
         return [out[off[i]:off[i + 1]] for i in range(len(seqs))]
 
+    def confusion_batch(self, pb):
+        """calc_confusion_matrices (bam.pyx:351-510) for the ranges of a confusion.PileupPack; returns int64
+        subs[5,5], nps[max_n,max_l+1,max_l+1], inss[max_l+1], dels[max_l+1] summed over the ranges."""
+        from ._lib import PileupBatch
+        T = self.params["max_l"] + 1
+        subs = np.zeros((5, 5), np.int64); nps = np.zeros((self.params["max_n"], T, T), np.int64)
+        inss = np.zeros(T, np.int64); dels = np.zeros(T, np.int64)
+        ptr = lambda a: a.ctypes.data if a is not None and a.size else None   # noqa: E731
+        b = PileupBatch(len(pb.range_start), ptr(pb.range_start), ptr(pb.range_end), ptr(pb.ref_ascii), pb.ref_off.ctypes.data,
+                        len(pb.read_pos), ptr(pb.read_pos), ptr(pb.seq_ascii), ptr(pb.qual), pb.seq_off.ctypes.data,
+                        ptr(pb.cigar_rle), pb.cigar_off.ctypes.data, ptr(pb.range_reads), pb.range_reads_off.ctypes.data,
+                        int(pb.min_base_q))
+        self._check(self._L.npore_confusion_batch(self._ctx, C.byref(b), subs.ctypes.data, nps.ctypes.data, inss.ctypes.data,
+                                                  dels.ctypes.data), "npore_confusion_batch")
+        return subs, nps, inss, dels
+
     # convenience: python objects in, python objects out
     def align_many(self, refs, seqs, cigars, standardize=False, collapse=False):
         """refs/seqs: lists of uint8 code arrays; cigars: CIGAR texts (run-length or expanded).

@@ -194,3 +194,91 @@ def fuzz_case(rng: np.random.Generator, call_model=None):
     r = int(rng.choice([3, 5, 10, 30]))
     max_b_rows = int(rng.choice([12, 20, 37, 50, 200, 20000]))
     return ref, seq, cig, r, max_b_rows
+
+
+def make_aligned_reads(ref: str, n_reads: int, read_len: int, rng: np.random.Generator, max_n: int = 6,
+                       p_tract: float = 0.3, with_clips: bool = True):
+    """Coordinate-sorted alignments against `ref` for the confusion-matrix path (bam.pyx:351-510): every read is
+    (pos, [(len, op)], seq, qual bytes | None, flag, mapq).  Unlike make_read, copy-number errors sit at the START of a
+    tract (where a left-aligning mapper reports them and where the reference counts them), and the script mixes in the
+    cases the pileup text is sensitive to: D next to I, I next to D, N read bases, low base qualities, reads without
+    qualities, reverse / secondary reads, soft clips and uncovered stretches."""
+    L = len(ref)
+    letters = "ACGT"
+    tract_at = {}
+    for s0, n0, c0 in _tracts(ref, max_n):
+        tract_at.setdefault(s0, (n0, c0))
+    reads = []
+    for _ in range(n_reads):
+        span = int(min(L, max(1, read_len + rng.integers(-read_len // 4, read_len // 4 + 1))))
+        pos = int(rng.integers(0, L - span + 1))
+        ops, seq = [], []
+
+        def emit(op, n, bases=""):
+            if n <= 0:
+                return
+            if ops and ops[-1][1] == op:
+                ops[-1][0] += n
+            else:
+                ops.append([n, op])
+            seq.append(bases)
+
+        eqx = rng.random() < 0.3                   # '=' / 'X' instead of 'M'
+        if with_clips and rng.random() < 0.15:
+            emit("H", int(rng.integers(1, 6)))
+        if with_clips and rng.random() < 0.3:
+            k = int(rng.integers(1, 6))
+            emit("S", k, "".join(rng.choice(list(letters), size=k)))
+            if rng.random() < 0.3:
+                emit("I", 2, "".join(rng.choice(list(letters), size=2)))
+        p, end = pos, pos + span
+        while p < end:
+            u = rng.random()
+            b = ref[p]
+            if u < 0.02:
+                b = letters[(letters.find(b) + int(rng.integers(1, 4))) % 4] if b in letters else "A"
+            elif u < 0.023:
+                b = "N"
+            elif u < 0.0235:
+                b = "R"                            # IUPAC code: the reference's parser abandons the pileup line there
+            emit(("=" if b == ref[p] else "X") if eqx else "M", 1, b)
+            p += 1
+            if p >= end:
+                break
+            tr = tract_at.get(p)
+            u = rng.random()
+            if tr is not None and u < p_tract:
+                n0, c0 = tr
+                k = int(rng.integers(1, 4))
+                if rng.random() < 0.5:
+                    d = min(k * n0, end - p - 1)
+                    emit("D", d)
+                    p += d
+                else:
+                    unit = ref[p:p + n0]
+                    ins = unit * k
+                    if rng.random() < 0.15:      # not a clean copy
+                        ins = ins[:-1] + letters[(letters.find(ins[-1]) + 1) % 4]
+                    emit("I", len(ins), ins)
+            elif u < 0.012:
+                d = min(int(rng.integers(1, 4)), end - p - 1)
+                emit("N" if rng.random() < 0.05 else "D", d)
+                p += d
+                if rng.random() < 0.25:           # D directly followed by I
+                    k = int(rng.integers(1, 3))
+                    emit("I", k, "".join(rng.choice(list(letters), size=k)))
+            elif u < 0.024:
+                k = int(rng.integers(1, 4))
+                emit("I", k, "".join(rng.choice(list(letters), size=k)))
+                if rng.random() < 0.25 and end - p > 3:   # I directly followed by D
+                    emit("D", 1)
+                    p += 1
+        if with_clips and rng.random() < 0.3:
+            k = int(rng.integers(1, 6))
+            emit("S", k, "".join(rng.choice(list(letters), size=k)))
+        s = "".join(seq)
+        qual = None if rng.random() < 0.1 else bytes(rng.integers(3, 41, size=len(s)).astype(np.uint8))
+        flag = (16 if rng.random() < 0.5 else 0) | (256 if rng.random() < 0.05 else 0) | (1024 if rng.random() < 0.02 else 0)
+        reads.append((pos, [(n, op) for n, op in ops], s, qual, flag, int(rng.integers(0, 61))))
+    reads.sort(key=lambda r: r[0])
+    return reads
