@@ -76,6 +76,7 @@ struct npore_ctx {
     // per sub-batch scratch
     DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_tb, d_rr_q, d_rr_ctl, d_rr_state;
     int rr_slice = 512;
+    DevBuf d_chunk_dst, d_part_cnt;
     DevBuf d_cm[22];                     // npore_confusion_batch staging (kept between calls)
     HostBuf h_small;
     int64_t pack_ops_total = 0, pack_rle_total = 0;
@@ -221,6 +222,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
                       &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
     for (auto *b : bufs) b->release();
     for (auto &b : ctx->d_cm) b.release();
+    ctx->d_chunk_dst.release(); ctx->d_part_cnt.release();
     ctx->h_small.release();
     for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto &e : ctx->sub_ev) cudaEventDestroy(e);
@@ -482,24 +484,39 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         fa.to_m = (flags & NPORE_OUT_STANDARDIZE) ? 1 : 0;
         fa.ops_off = ctx->d_ops_off.as<int64_t>(); fa.rle_off = ctx->d_rle_off.as<int64_t>();
         fa.pack_ops = ctx->d_pack_ops.as<uint8_t>(); fa.pack_rle = ctx->d_pack_rle.as<uint32_t>();
-        gather_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
+        int max_ops = 1;
+        for (const ItemDesc &I : ctx->items) max_ops = std::max(max_ops, I.total_ops);
+        const int parts = std::min(FIN_MAX_PARTS, (max_ops + 32767) / 32768);
+        CU(ctx->d_chunk_dst.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ctx->n_chunks, 1)));
+        CU(ctx->d_part_cnt.ensure(sizeof(int32_t) * (size_t)n * parts));
+        fa.chunks = ctx->d_chunks.as<ChunkDesc>(); fa.n_chunks = (int)ctx->n_chunks;
+        fa.chunk_dst = ctx->d_chunk_dst.as<int32_t>(); fa.parts = parts; fa.part_cnt = ctx->d_part_cnt.as<int32_t>();
+        const dim3 grid_np(n, parts);
+        item_len_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
         CU(cudaGetLastError()); S.launches++;
-        if (need_rle) {
-            rle_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
+        if (ctx->n_chunks) {
+            gather_kernel<<<(unsigned)ctx->n_chunks, FIN_THREADS, 0, ctx->stream>>>(fa);
             CU(cudaGetLastError()); S.launches++;
+        }
+        if (need_rle) {
+            if (parts > 1) { rle_count_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa); S.launches++; }
+            rle_start_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa);
+            rle_word_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa);
+            CU(cudaGetLastError()); S.launches += 2;
         } else CU(cudaMemsetAsync(ctx->d_rle_len.p, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
         if (flags & NPORE_OUT_STANDARDIZE) {
             standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa);
             CU(cudaGetLastError()); S.launches++;
             if (want_ops) {
-                expand_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa);
+                if (parts > 1) { expand_count_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa); S.launches++; }
+                expand_fill_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa);
                 CU(cudaGetLastError()); S.launches++;
             }
         }
         scan_kernel<<<1, 1024, 0, ctx->stream>>>(fa);
         CU(cudaGetLastError()); S.launches++;
         if (want_ops || want_rle) {
-            pack_kernel<<<n, FIN_THREADS, 0, ctx->stream>>>(fa, want_ops ? 1 : 0, want_rle ? 1 : 0);
+            pack_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa, want_ops ? 1 : 0, want_rle ? 1 : 0);
             CU(cudaGetLastError()); S.launches++;
         }
         // per-item sizes / status / chunk results travel with the run so that download() knows exact sizes

@@ -1,23 +1,31 @@
 // finish.cuh -- per-item epilogue on device:
-//   gather_kernel        concatenates the chunks' op strings (aln.pyx:742 `full_aln += aln[::-1]`)
-//   rle_kernel           src/cig.pyx:13-38 collapse_cigar as BAM-style words (len<<4 | op); with `to_m` set X and = are
+//   item_len / gather    concatenate the chunks' op strings (aln.pyx:742 `full_aln += aln[::-1]`), one CTA per chunk
+//   rle_* kernels        src/cig.pyx:13-38 collapse_cigar as BAM-style words (len<<4 | op); with `to_m` set X and = are
 //                        first mapped to M (bam.pyx:65)
 //   standardize_kernel   src/bam.pyx:65-78 in the RUN-LENGTH domain: push_indels_left(D, ref); push_inss_thru_dels;
 //                        push_indels_left(I, seq); push_inss_thru_dels (src/cig.pyx:102-192; the reference's `while True`
 //                        body runs exactly once because old_cig aliases int_cig); 'ID' -> 'M'.  Each pass is one
 //                        sequential sweep over the item's groups with a stack-like output (O(#groups), ~1000 per 10 kb
 //                        read, instead of the reference's 4 sweeps over every op), one warp (lane 0) per item.
-//   expand_kernel        run-length words -> one char per op (the expanded 'MID' string realign_hap returns)
+//   expand_* kernels     run-length words -> one char per op (the expanded 'MID' string realign_hap returns)
 //   scan / pack kernels  exclusive prefix of the per-item output sizes and a dense copy, so that the D2H transfer moves
 //                        exactly the bytes the caller gets.
 #pragma once
 #include "common.cuh"
 
 #define FIN_THREADS 128
+#define FIN_WIDE 256             // threads of the part-parallel kernels
+#define FIN_MAX_PARTS 64
 
+// Items differ in size by four orders of magnitude (a 10 kb read has 2e4 ops, a whole-contig haplotype 1e8): every
+// per-item kernel below runs on a grid (items, parts) and a CTA handles the part-th slice of its item; `parts` is chosen
+// on the host from the largest item (1 for read batches).  Slices that need a running count across the item (group
+// indices, output offsets) get it from a small counting pass (part_cnt) summed over the preceding parts.
 struct FinishArgs {
     const ItemDesc *items; int n_items;
+    const ChunkDesc *chunks; int n_chunks;
     const ChunkOut *chunk_out;
+    int32_t *chunk_dst;           // per chunk: offset of its piece inside the item's op string
     const uint8_t *scratch;       // right-aligned chunk pieces
     uint8_t *ops;                 // per-item op strings (item region at out_off)
     int32_t *item_len;            // ops per item
@@ -27,30 +35,76 @@ struct FinishArgs {
     int32_t *rle_len;
     int32_t *rle_which;           // 0: result in rleA, 1: in rleB
     int to_m;
+    int parts; int32_t *part_cnt; // [n_items * parts]
     // packing
     int64_t *ops_off, *rle_off;   // [n+1] exclusive prefixes (device)
     uint8_t *pack_ops; uint32_t *pack_rle;
 };
 
-__global__ void __launch_bounds__(FIN_THREADS) gather_kernel(const FinishArgs a)
+// block-wide inclusive scan of one int per thread; returns the inclusive value, `total` = sum over the block.
+// s_w: shared int[blockDim/32].  Ends with a barrier, so s_w can be reused by the next call.
+template <int THREADS>
+__device__ __forceinline__ int fin_block_scan(int v, int *s_w, int &total)
 {
-    __shared__ int s_status;
-    const int it = blockIdx.x;
-    if (it >= a.n_items) return;
-    const ItemDesc &I = a.items[it];
-    if (threadIdx.x == 0) s_status = I.status;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(NP_FULL, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[wid] = x;
     __syncthreads();
-    uint8_t *dst = a.ops + I.out_off;
-    const uint8_t *src = a.scratch + I.out_off;
-    int off = 0;
-    for (int k = 0; k < I.n_chunks; k++) {
-        const ChunkOut co = a.chunk_out[I.chunk_first + k];
-        for (int t = threadIdx.x; t < co.len; t += FIN_THREADS) dst[off + t] = src[co.start + t];
-        if (threadIdx.x == 0 && co.status && !s_status) s_status = co.status;
-        off += co.len;
+    int pre = 0, tot = 0;
+#pragma unroll
+    for (int q = 0; q < THREADS / 32; q++) { const int t = s_w[q]; if (q < wid) pre += t; tot += t; }
+    __syncthreads();
+    total = tot;
+    return pre + x;
+}
+
+__device__ __forceinline__ void fin_slice(int n, int parts, int part, int &lo, int &hi)
+{
+    const int per = (n + parts - 1) / parts;
+    lo = min(n, part * per); hi = min(n, lo + per);
+}
+
+// where each chunk's op string goes inside its item (aln.pyx:742 `full_aln += aln[::-1]`), the item's length and status
+__global__ void __launch_bounds__(FIN_THREADS) item_len_kernel(const FinishArgs a)
+{
+    __shared__ int s_w[FIN_THREADS / 32];
+    __shared__ int s_first;
+    const int it = blockIdx.x;
+    const ItemDesc &I = a.items[it];
+    if (threadIdx.x == 0) s_first = 0x7fffffff;
+    __syncthreads();
+    int carry = 0;
+    for (int base = 0; base < I.n_chunks; base += FIN_THREADS) {
+        const int k = base + threadIdx.x;
+        int len = 0;
+        if (k < I.n_chunks) {
+            const ChunkOut co = a.chunk_out[I.chunk_first + k];
+            len = co.len;
+            if (co.status) atomicMin(&s_first, k);
+        }
+        int tot;
+        const int x = fin_block_scan<FIN_THREADS>(len, s_w, tot);
+        if (k < I.n_chunks) a.chunk_dst[I.chunk_first + k] = carry + x - len;
+        carry += tot;
     }
     __syncthreads();
-    if (threadIdx.x == 0) { a.item_len[it] = off; a.item_status[it] = s_status; }
+    if (threadIdx.x == 0) {
+        a.item_len[it] = carry;
+        a.item_status[it] = I.status ? I.status : (s_first != 0x7fffffff ? a.chunk_out[I.chunk_first + s_first].status : 0);
+    }
+}
+
+// one CTA per chunk: copy the chunk's op string to its place
+__global__ void __launch_bounds__(FIN_THREADS) gather_kernel(const FinishArgs a)
+{
+    const int c = blockIdx.x;
+    const ItemDesc &I = a.items[a.chunks[c].item];
+    const ChunkOut co = a.chunk_out[c];
+    uint8_t *dst = a.ops + I.out_off + a.chunk_dst[c];
+    const uint8_t *src = a.scratch + I.out_off + co.start;
+    for (int t = threadIdx.x; t < co.len; t += FIN_THREADS) dst[t] = src[t];
 }
 
 __device__ __forceinline__ uint32_t op_code(uint8_t ch, int to_m)
@@ -61,42 +115,70 @@ __device__ __forceinline__ uint32_t op_code(uint8_t ch, int to_m)
     return ch == '=' ? 7u : 8u;                                   // cfg.py:28-32
 }
 
-// expanded chars -> run-length words, one CTA per item: boundary flags, block scan, starts, lengths
-__global__ void __launch_bounds__(FIN_THREADS) rle_kernel(const FinishArgs a)
+// ---- expanded chars -> run-length words (cig.pyx:13-38) in three part-parallel steps
+// (1) group starts per slice
+__global__ void __launch_bounds__(FIN_WIDE) rle_count_kernel(const FinishArgs a)
 {
-    __shared__ int s_warp[FIN_THREADS / 32];
-    __shared__ int s_carry;
-    const int it = blockIdx.x;
-    if (it >= a.n_items) return;
+    __shared__ int s_w[FIN_WIDE / 32];
+    const int it = blockIdx.x, part = blockIdx.y;
+    const uint8_t *c = a.ops + a.items[it].out_off;
+    int lo, hi;
+    fin_slice(a.item_len[it], a.parts, part, lo, hi);
+    int cnt = 0;
+    for (int k = lo + threadIdx.x; k < hi; k += FIN_WIDE) cnt += (k == 0) || (op_code(c[k], a.to_m) != op_code(c[k - 1], a.to_m));
+    int tot;
+    fin_block_scan<FIN_WIDE>(cnt, s_w, tot);
+    if (threadIdx.x == 0) a.part_cnt[it * a.parts + part] = tot;
+}
+
+// (2) start position of every group -> rleB (scratch); 4 consecutive ops per thread
+__global__ void __launch_bounds__(FIN_WIDE) rle_start_kernel(const FinishArgs a)
+{
+    __shared__ int s_w[FIN_WIDE / 32];
+    const int it = blockIdx.x, part = blockIdx.y;
     const ItemDesc &I = a.items[it];
     const uint8_t *c = a.ops + I.out_off;
-    uint32_t *w = a.rleA + I.out_off, *startp = a.rleB + I.out_off;    // rleB: start position of group g (scratch)
-    const int n = a.item_len[it];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < n; base += FIN_THREADS) {
-        const int k = base + threadIdx.x;
-        int flag = 0;
-        if (k < n) flag = (k == 0) || (op_code(c[k], a.to_m) != op_code(c[k - 1], a.to_m));
-        int x = flag;
+    uint32_t *startp = a.rleB + I.out_off;
+    int lo, hi;
+    fin_slice(a.item_len[it], a.parts, part, lo, hi);
+    int carry = 0;
+    if (a.parts > 1) for (int q = 0; q < part; q++) carry += a.part_cnt[it * a.parts + q];
+    for (int base = lo; base < hi; base += FIN_WIDE * 4) {
+        const int k0 = base + threadIdx.x * 4;
+        uint32_t prev = (k0 > 0 && k0 < hi) ? op_code(c[k0 - 1], a.to_m) : 0xffu;
+        uint32_t fl = 0u;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(NP_FULL, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        int pre = s_carry;
-        for (int q = 0; q < wid; q++) pre += s_warp[q];
-        if (flag) startp[pre + x - 1] = (uint32_t)k;
-        __syncthreads();
-        if (threadIdx.x == FIN_THREADS - 1) s_carry = pre + x;
-        __syncthreads();
+        for (int j = 0; j < 4; j++) {
+            if (k0 + j < hi) {
+                const uint32_t o = op_code(c[k0 + j], a.to_m);
+                if (o != prev) fl |= 1u << j;
+                prev = o;
+            }
+        }
+        int tot;
+        int at = carry + fin_block_scan<FIN_WIDE>(__popc(fl), s_w, tot) - __popc(fl);
+#pragma unroll
+        for (int j = 0; j < 4; j++) if ((fl >> j) & 1u) startp[at++] = (uint32_t)(k0 + j);
+        carry += tot;
     }
-    const int m = s_carry;
-    for (int g = threadIdx.x; g < m; g += FIN_THREADS) {
+    if (part == a.parts - 1 && threadIdx.x == 0) { a.rle_len[it] = carry; a.rle_which[it] = 0; }
+}
+
+// (3) words from consecutive starts
+__global__ void __launch_bounds__(FIN_WIDE) rle_word_kernel(const FinishArgs a)
+{
+    const int it = blockIdx.x;
+    const ItemDesc &I = a.items[it];
+    const uint8_t *c = a.ops + I.out_off;
+    uint32_t *w = a.rleA + I.out_off;
+    const uint32_t *startp = a.rleB + I.out_off;
+    const int n = a.item_len[it], m = a.rle_len[it];
+    int lo, hi;
+    fin_slice(m, a.parts, blockIdx.y, lo, hi);
+    for (int g = lo + threadIdx.x; g < hi; g += FIN_WIDE) {
         const uint32_t st = startp[g], en = (g + 1 < m) ? startp[g + 1] : (uint32_t)n;
         w[g] = ((en - st) << 4) | op_code(c[st], a.to_m);
     }
-    if (threadIdx.x == 0) { a.rle_len[it] = m; a.rle_which[it] = 0; }
 }
 
 // ---- stack-like output list of run-length groups (merges equal neighbours, drops empty groups)
@@ -184,37 +266,53 @@ __global__ void __launch_bounds__(FIN_THREADS) standardize_kernel(const FinishAr
     a.rle_len[it] = m; a.rle_which[it] = 1; a.item_len[it] = tot;
 }
 
-// run-length words -> chars, one CTA per item
-__global__ void __launch_bounds__(FIN_THREADS) expand_kernel(const FinishArgs a)
+// ---- run-length words -> chars (the expanded 'MID' string realign_hap returns), two part-parallel steps
+__global__ void __launch_bounds__(FIN_WIDE) expand_count_kernel(const FinishArgs a)
 {
-    __shared__ int s_warp[FIN_THREADS / 32];
-    __shared__ int s_carry;
-    const int it = blockIdx.x;
-    if (it >= a.n_items) return;
+    __shared__ int s_w[FIN_WIDE / 32];
+    const int it = blockIdx.x, part = blockIdx.y;
+    const uint32_t *w = (a.rle_which[it] ? a.rleB : a.rleA) + a.items[it].out_off;
+    int lo, hi;
+    fin_slice(a.rle_len[it], a.parts, part, lo, hi);
+    int cnt = 0;
+    for (int g = lo + threadIdx.x; g < hi; g += FIN_WIDE) cnt += (int)(w[g] >> 4);
+    int tot;
+    fin_block_scan<FIN_WIDE>(cnt, s_w, tot);
+    if (threadIdx.x == 0) a.part_cnt[it * a.parts + part] = tot;
+}
+
+// short groups are written by their own thread, long ones (haplotype-sized M runs) by a whole warp
+__global__ void __launch_bounds__(FIN_WIDE) expand_fill_kernel(const FinishArgs a)
+{
+    __shared__ int s_w[FIN_WIDE / 32];
+    __shared__ int s_long[FIN_WIDE][2];
+    __shared__ int s_nlong;
+    const int it = blockIdx.x, part = blockIdx.y;
     const ItemDesc &I = a.items[it];
     const uint32_t *w = (a.rle_which[it] ? a.rleB : a.rleA) + I.out_off;
     uint8_t *c = a.ops + I.out_off;
-    const int m = a.rle_len[it];
+    int lo, hi;
+    fin_slice(a.rle_len[it], a.parts, part, lo, hi);
+    int carry = 0;
+    if (a.parts > 1) for (int q = 0; q < part; q++) carry += a.part_cnt[it * a.parts + q];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (int base = 0; base < m; base += FIN_THREADS) {
+    for (int base = lo; base < hi; base += FIN_WIDE) {
         const int g = base + threadIdx.x;
-        const uint32_t word = g < m ? w[g] : 0u;
+        const uint32_t word = g < hi ? w[g] : 0u;
         const int len = (int)(word >> 4);
-        int x = len;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(NP_FULL, x, o); if (lane >= o) x += y; }
-        if (lane == 31) s_warp[wid] = x;
+        if (threadIdx.x == 0) s_nlong = 0;
+        int tot;
+        const int start = carry + fin_block_scan<FIN_WIDE>(len, s_w, tot) - len;      // (barrier inside: s_nlong visible)
+        if (len > 16) { const int q = atomicAdd(&s_nlong, 1); s_long[q][0] = start; s_long[q][1] = (int)word; }
+        else { const uint8_t ch = "MIDNSHP=XB"[word & 15u]; for (int t = 0; t < len; t++) c[start + t] = ch; }
         __syncthreads();
-        int pre = s_carry;
-        for (int q = 0; q < wid; q++) pre += s_warp[q];
-        const int start = pre + x - len;
-        const uint8_t ch = "MIDNSHP=XB"[word & 15u];
-        for (int t = 0; t < len; t++) c[start + t] = ch;
+        for (int q = wid; q < s_nlong; q += FIN_WIDE / 32) {
+            const int st = s_long[q][0], ln = s_long[q][1] >> 4;
+            const uint8_t ch = "MIDNSHP=XB"[s_long[q][1] & 15];
+            for (int t = lane; t < ln; t += 32) c[st + t] = ch;
+        }
         __syncthreads();
-        if (threadIdx.x == FIN_THREADS - 1) s_carry = pre + x;
-        __syncthreads();
+        carry += tot;
     }
 }
 
@@ -247,19 +345,19 @@ __global__ void __launch_bounds__(1024) scan_kernel(const FinishArgs a)
     if (threadIdx.x == 0) { a.ops_off[a.n_items] = s_carry[0]; a.rle_off[a.n_items] = s_carry[1]; }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS) pack_kernel(const FinishArgs a, int want_ops, int want_rle)
+__global__ void __launch_bounds__(FIN_WIDE) pack_kernel(const FinishArgs a, int want_ops, int want_rle)
 {
     const int it = blockIdx.x;
-    if (it >= a.n_items) return;
     const ItemDesc &I = a.items[it];
+    int lo, hi;
     if (want_ops) {
         const uint8_t *src = a.ops + I.out_off; uint8_t *dst = a.pack_ops + a.ops_off[it];
-        const int n = a.item_len[it];
-        for (int t = threadIdx.x; t < n; t += FIN_THREADS) dst[t] = src[t];
+        fin_slice(a.item_len[it], a.parts, blockIdx.y, lo, hi);
+        for (int t = lo + threadIdx.x; t < hi; t += FIN_WIDE) dst[t] = src[t];
     }
     if (want_rle) {
         const uint32_t *src = (a.rle_which[it] ? a.rleB : a.rleA) + I.out_off; uint32_t *dst = a.pack_rle + a.rle_off[it];
-        const int m = a.rle_len[it];
-        for (int t = threadIdx.x; t < m; t += FIN_THREADS) dst[t] = src[t];
+        fin_slice(a.rle_len[it], a.parts, blockIdx.y, lo, hi);
+        for (int t = lo + threadIdx.x; t < hi; t += FIN_WIDE) dst[t] = src[t];
     }
 }
