@@ -123,15 +123,16 @@ inline int chunks_of(int total, int max_b_rows)
 template <int CPL>
 int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 {
-    const size_t smem = (size_t)(FWD_WARPS + FWD_ALIGNED) * 4 * NP_RING * 32 * CPL * sizeof(float);
+    constexpr int WARPS = fwd_warps(CPL);
+    const size_t smem = (size_t)(WARPS + FWD_ALIGNED) * 4 * NP_RING * 32 * CPL * sizeof(float);
     CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, FWD_WARPS * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    ctx->stats.overflow_runs = per_sm * FWD_WARPS;      // resident forward warps per SM (diagnostic)
-    int grid = std::min((n_sub + FWD_WARPS - 1) / FWD_WARPS, ctx->sm_count * per_sm);
+    ctx->stats.overflow_runs = per_sm * WARPS;      // resident forward warps per SM (diagnostic)
+    int grid = std::min((n_sub + WARPS - 1) / WARPS, ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
-    forward_kernel<CPL><<<grid, FWD_WARPS * 32, smem, ctx->stream>>>(fa);
+    forward_kernel<CPL><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);
     CU(cudaGetLastError());
     return NPORE_OK;
 }

@@ -33,6 +33,10 @@
 #ifndef FWD_WARPS
 #define FWD_WARPS 4
 #endif
+#ifndef FWD_WARPS_WIDE
+#define FWD_WARPS_WIDE 6   // wide bands (CPL >= 4): a ring is 16-32 KB per warp, so fewer, larger CTAs waste less of the
+#endif                     // shared memory on the alignment slack (6+1 rings of 32 KB = 224 KB fill one SM at CPL = 8)
+static __host__ __device__ constexpr int fwd_warps(int cpl) { return cpl >= 4 ? FWD_WARPS_WIDE : FWD_WARPS; }
 
 #ifndef FWD_ALIGNED
 #define FWD_ALIGNED 1   // 1: rings aligned to their size (one ring of slack per CTA), cell address = offset | base
@@ -97,6 +101,11 @@ static void fwd_init_constants()
     cudaMemcpyToSymbol(c_sipack, h, sizeof(h));
 }
 
+// run-queue words are polled with L2-only loads: a volatile (system-scope) load from a spinning warp costs every other
+// warp of the SM its L1 contents (measured: one waiting warp made a lone chunk 3x slower)
+__device__ __forceinline__ int ld_cg_poll(const int *p)
+{ int v; asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
 // ---- explicit shared-memory access by 32-bit byte address (keeps address arithmetic to what is written here)
 __device__ __forceinline__ float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 template <int OFF> __device__ __forceinline__ uint32_t lds_u_off(uint32_t a)
@@ -157,11 +166,11 @@ __device__ __forceinline__ void shr_eval(uint32_t D, bool pred, uint32_t dsh, ui
 #endif
 template <int CPL>
 #if FWD_MAXREG
-__global__ void __launch_bounds__(FWD_WARPS * 32) __maxnreg__(CPL <= 2 ? FWD_MAXREG : 255) forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(fwd_warps(CPL) * 32) __maxnreg__(CPL <= 2 ? FWD_MAXREG : 255) forward_kernel(const ForwardArgs a)
 #elif FWD_MINB > 1
-__global__ void __launch_bounds__(FWD_WARPS * 32, (CPL <= 2 ? FWD_MINB : CPL <= 4 ? 12 : 8) / FWD_WARPS) forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(fwd_warps(CPL) * 32, (CPL <= 2 ? FWD_MINB : CPL <= 4 ? 12 : 8) / fwd_warps(CPL)) forward_kernel(const ForwardArgs a)
 #else
-__global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const ForwardArgs a)
 #endif
 {
     constexpr int NC = 32 * CPL;
@@ -171,7 +180,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
     __shared__ float s_sub[64];
     __shared__ uint2 s_lut[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t = threadIdx.x; t < 64; t += FWD_WARPS * 32) {
+    for (int t = threadIdx.x; t < 64; t += fwd_warps(CPL) * 32) {
         const int sb = t >> 3, rb = t & 7;
         s_sub[t] = (sb < 5 && rb < 5) ? a.sub_tab[sb * 5 + rb] : 0.f;
     }
@@ -205,16 +214,18 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             int pos = 0;
             if (lane == 0) {
                 pos = atomicAdd(a.rr_ctl, 1);
-                volatile int *qp = a.rr_q + (pos & a.rr_mask);
+                int *qp = a.rr_q + (pos & a.rr_mask);
                 int v;
-                while ((v = *qp) < 0) {
-                    if (*(volatile int *)(a.rr_ctl + 2) >= a.n) { v = -2; break; }
+                unsigned ns = FWD_SPIN_NS;
+                while ((v = ld_cg_poll(qp)) < 0) {
+                    if (ld_cg_poll(a.rr_ctl + 2) >= a.n) { v = -2; break; }
 #ifdef FWD_SPIN_DEBUG
                     atomicAdd(a.rr_ctl + 8, 1);
 #endif
-                    __nanosleep(FWD_SPIN_NS);
+                    __nanosleep(ns);
+                    if (ns < 4096u) ns <<= 1;
                 }
-                if (v >= 0) *qp = -1;
+                if (v >= 0) __stcg(qp, -1);
                 idx = v;
             }
             idx = __shfl_sync(NP_FULL, idx, 0);
@@ -294,12 +305,22 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
         // steady state = every cell with 1 <= b_col <= 2r-1 is an interior cell with i >= 2 and j >= 2
         const int idLo = r + 1, idSpan = imax - 2 * r, ddSpan = jmax - 2 * r;
 #if FWD_RR
-        const int dEnd = min(B, d0 + a.rr_slice);
+        int dEnd = min(B, d0 + a.rr_slice);
 #else
         const int dEnd = B;
 #endif
 
-        for (int d = d0; d < dEnd; d++) {
+        for (int d = d0; ; d++) {
+            if (d >= dEnd) {
+                if (dEnd >= B) break;
+#if FWD_RR
+                // slice over: hand the chunk back only if another chunk is waiting for a warp (tail - head > 0)
+                int queued = 0;
+                if (lane == 0) queued = ld_cg_poll(a.rr_ctl + 1) - ld_cg_poll(a.rr_ctl);
+                if (__shfl_sync(NP_FULL, queued, 0) > 0) break;
+                dEnd = min(B, dEnd + a.rr_slice);
+#endif
+            }
             float lMv[CPL], lDv[CPL]; int lMr[CPL];
             if (d > 0) {
                 const int g = c.brk + d - 1;                 // op that leads to this anti-diagonal
@@ -542,7 +563,7 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) forward_kernel(const ForwardAr
             __syncwarp();
             if (lane == 0) {
                 const int p2 = atomicAdd(a.rr_ctl + 1, 1);
-                *(volatile int *)(a.rr_q + (p2 & a.rr_mask)) = idx;
+                __stcg(a.rr_q + (p2 & a.rr_mask), idx);
             }
             continue;
         }
