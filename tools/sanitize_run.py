@@ -19,5 +19,32 @@ for (r, mb) in [(30, 200), (10, 37), (30, 20000)]:
     bad += sum(o != c["out"] or s != c["std"] for o, s, c in zip(outs, std, cases))
     eng.get_np_info(refs[0])
     eng.close()
+# a long item (several finish parts), expanded + run-length outputs, wide band (6-warp CTAs)
+rng = np.random.default_rng(3)
+cm = synth.call_length_model(NP)
+ref, tr = synth.make_reference_with_tracts(60_000, rng)
+rd = synth.make_reads(ref, 1, 45_000, rng, cm, tracts=tr)[0]
+from npore_b200 import cig
+for r, mb in ((30, 20000), (60, 5000)):
+    eng = Realigner(S, NP, max_b_rows=mb, r=r)
+    ir, iq = oracle.bases_to_int(rd[9]), oracle.bases_to_int(rd[7])
+    o, _, _ = eng.align_many([ir], [iq], [cig.expand_cigar(rd[5])], standardize=True)
+    c, _, _ = eng.align_many([ir], [iq], [cig.expand_cigar(rd[5])], standardize=True, collapse=True)
+    want = oracle.standardize(oracle.align(ir, iq, cig.expand_cigar(rd[5]), S, NP, max_b_rows=mb, r=r), ir, iq)
+    bad += (o[0] != want) + (c[0] != oracle.collapse_cigar(want))
+    eng.close()
+# confusion matrices
+import pileup_oracle as po
+from npore_b200 import confusion
+contig = synth.make_reference(3000, rng, p_np=0.4)
+reads = synth.make_aligned_reads(contig, 80, 400, rng)
+want = po.confusion([po.Read(*r) for r in reads], contig, 100, 2900, oracle.get_np_info, oracle.bases_to_int)
+got = confusion.calc_confusion_matrices_batch([("c", 100, 1500), ("c", 1500, 2900)], refs={"c": contig},
+                                              reads={"c": confusion.AlignedReads([r[:5] for r in reads])})
+want2 = None
+for a, b in ((100, 1500), (1500, 2900)):
+    one = po.confusion([po.Read(*r) for r in reads], contig, a, b, oracle.get_np_info, oracle.bases_to_int)
+    want2 = one if want2 is None else tuple(x + y for x, y in zip(want2, one))
+bad += sum(not np.array_equal(a, b) for a, b in zip(want2, got))
 print("sanitize_run mismatches:", bad)
 sys.exit(1 if bad else 0)
