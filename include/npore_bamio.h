@@ -1,0 +1,74 @@
+/*
+ * npore_bamio.h -- native BAM ingest and SAM record output for the realignment path (part of libnpore_b200.so).
+ *
+ * These entry points replace, for this path only, what the reference gets from pysam / htslib (a compiled
+ * third-party dependency, not part of the TimD1/nPoRe tree):
+ *
+ *   npore_bam_open / _columns / _gather  <- pysam.AlignmentFile(bam).fetch(...) and the per-read attribute reads of
+ *                                           src/bam.pyx:18-47 get_read_data(): flag, reference_start, reference_length,
+ *                                           mapping_quality, cigar, query_alignment_sequence / _qualities (soft clips
+ *                                           removed), HP tag.  BGZF members are inflated on n_threads host threads.
+ *   npore_sam_format                     <- the record print of src/bam.pyx:81-84 realign_read():
+ *                                           name flag rname start+1 mapq CIGAR * 0 (stop-start) seq quals HP:i:hap
+ *                                           for a whole batch, in input order, from the run-length words the GPU returns.
+ *
+ * Plain C ABI; all pointers are caller-owned host memory.  Functions return 0 or a negative code; the text of the last
+ * error of the calling thread is npore_io_last_error().  No CUDA involved.
+ */
+#ifndef NPORE_BAMIO_H
+#define NPORE_BAMIO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct npore_bam npore_bam;
+
+#define NPORE_IO_OK         0
+#define NPORE_IO_ERR_OPEN  -1   /* file missing / unreadable                      */
+#define NPORE_IO_ERR_FORMAT -2  /* not BGZF / not BAM / truncated / CRC mismatch  */
+#define NPORE_IO_ERR_ARG   -3
+
+const char *npore_io_last_error(void);
+
+/* read the whole file, inflate its BGZF blocks on n_threads threads (<= 0: all cores), index the records */
+int      npore_bam_open(const char *path, int n_threads, npore_bam **out);
+void     npore_bam_close(npore_bam *b);
+int64_t  npore_bam_header_text(const npore_bam *b, const char **text);          /* returns the text length */
+int32_t  npore_bam_n_refs(const npore_bam *b);
+int      npore_bam_ref(const npore_bam *b, int32_t i, const char **name, int64_t *length);
+int64_t  npore_bam_n_records(const npore_bam *b);
+
+/* one value per record, file order.  end = pos + reference span of the CIGAR (M D N = X); aln_len = SEQ length without
+ * the soft-clipped ends (pysam query_alignment_sequence); n_cigar = CIGAR words once S and H are dropped (bam.pyx:59);
+ * hp = value of the HP tag or 0 (bam.pyx:46); has_qual = 0 when QUAL is stored as 0xff.  Any pointer may be NULL. */
+int      npore_bam_columns(const npore_bam *b, int32_t *ref_id, int32_t *pos, int32_t *end, int32_t *flag, int32_t *mapq,
+                           int32_t *aln_len, int32_t *n_cigar, int32_t *name_len, int32_t *hp, int32_t *has_qual);
+
+/* copy the selected records (indices into file order) into flat arrays.  The three offset arrays [n_sel+1] are the
+ * caller's exclusive prefix sums of aln_len / n_cigar / name_len over the selection.  seq_ascii is upper-cased;
+ * seq_codes uses N A C G T = 0..4 (anything else 0, src/cig.pyx:212-229); qual_ascii is phred+33 (unspecified bytes when
+ * has_qual == 0); cigar words keep BAM op codes.  Any output pointer may be NULL. */
+int      npore_bam_gather(const npore_bam *b, int64_t n_sel, const int64_t *sel, int n_threads,
+                          uint8_t *seq_ascii, uint8_t *seq_codes, uint8_t *qual_ascii, const int64_t *seq_off,
+                          uint32_t *cigar, const int64_t *cig_off, uint8_t *names, const int64_t *name_off);
+
+/* src/bam.pyx:83 for n records.  ref_names / ref_name_off: concatenated contig names; rle / rle_off: the collapsed CIGAR of
+ * every record as (len<<4|op) words (npore_result.rle).  has_qual[i] == 0 or an empty sequence prints '*' for QUAL.
+ * Returns the number of bytes written to out (each record ends in '\n'), or a negative code; out_capacity must be at
+ * least npore_sam_bound(...). */
+int64_t  npore_sam_bound(int64_t n, const int64_t *name_off, const int64_t *seq_off, const int64_t *rle_off, int64_t max_ref_name);
+int64_t  npore_sam_format(int64_t n, int n_threads,
+                          const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
+                          const uint8_t *ref_names, const int64_t *ref_name_off,
+                          const int32_t *pos, const int32_t *end, const int32_t *mapq,
+                          const uint32_t *rle, const int64_t *rle_off,
+                          const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
+                          const int32_t *hp, uint8_t *out, int64_t out_capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPORE_BAMIO_H */

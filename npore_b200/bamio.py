@@ -8,9 +8,13 @@
                                  get_reference_sequence().upper() yields)
   create_header(...)             bam.pyx:127-145: @HD VN:1.6 SO:coordinate, @SQ per contig, @PG realigner
   write_bam(path, ...)           minimal BGZF/BAM writer (fixtures for the tests; records in input order)
-  realign_bam(...)               ingest -> GPU batches -> ordered SAM: what realign.py:75-115 does end to end
-Host code only; the GPU path is entered through npore_b200.bam.realign_reads.
+  realign_bam(...)               ingest -> GPU batches -> ordered SAM: what realign.py:75-115 does end to end.  Uses the
+                                 native reader / writer of libnpore_b200.so (include/npore_bamio.h: multi-threaded BGZF
+                                 inflate, record decode into flat arrays, batch SAM formatting) and never builds
+                                 per-read Python objects; the pure-Python functions above remain as the tuple API.
+The GPU path is entered through npore_b200.engine (realign_bam) or npore_b200.bam.realign_reads (tuples).
 """
+import ctypes as C
 import gzip
 import io
 import os
@@ -24,7 +28,7 @@ from . import cfg
 
 _SEQ16 = "=ACMGRSVTWYHKDBN"
 _OPS = "MIDNSHP=XB"
-_SEQ_PAIR = np.array([a + b for a in _SEQ16 for b in _SEQ16])
+_SEQ_PAIR = np.frombuffer("".join(a + b for a in _SEQ16 for b in _SEQ16).encode(), dtype=np.uint8).reshape(256, 2)
 
 
 def read_fasta(path):
@@ -93,7 +97,7 @@ def read_bam(path):
             name = data[q:q + l_read_name - 1].decode(); q += l_read_name
             cig = np.frombuffer(data, dtype="<u4", count=n_cigar, offset=q); q += 4 * n_cigar
             packed = np.frombuffer(data, dtype=np.uint8, count=(l_seq + 1) // 2, offset=q); q += (l_seq + 1) // 2
-            seq = "".join(_SEQ_PAIR[packed])[:l_seq]
+            seq = _SEQ_PAIR[packed].tobytes()[:l_seq].decode("latin-1")
             qual = np.frombuffer(data, dtype=np.uint8, count=l_seq, offset=q); q += l_seq
             tags = _parse_tags(data[q:p + block_size])
             yield {"name": name, "flag": flag, "ref_id": ref_id, "pos": pos, "mapq": mapq, "cigar": cig, "seq": seq,
@@ -132,7 +136,9 @@ def get_read_data(bam_fn, fasta, regions=None, max_reads=0):
             lead = int(lens[0]) if len(ops) and ops[0] == 4 else (int(lens[1]) if len(ops) > 1 and ops[0] == 5 and ops[1] == 4 else 0)
             trail = int(lens[-1]) if len(ops) and ops[-1] == 4 else (int(lens[-2]) if len(ops) > 1 and ops[-1] == 5 and ops[-2] == 4 else 0)
             seq = r["seq"][lead:len(r["seq"]) - trail]
-            quals = "*" if r["qual"] is None else "".join(chr(33 + int(x)) for x in r["qual"][lead:len(r["qual"]) - trail])
+            quals = "*" if r["qual"] is None else (r["qual"][lead:len(r["qual"]) - trail] + np.uint8(33)).tobytes().decode("latin-1")
+            if not quals:
+                quals = "*"                                             # bam.pyx:42: an empty quality array is falsy
             hp = r["tags"].get("HP")
             kept += 1
             yield (r["name"], r["flag"], rname, rstart, r["mapq"], _cigar_string(r["cigar"]), rstop, seq.upper(), quals,
@@ -150,15 +156,159 @@ def create_header(outfile, refs, argv=None):
         fh.write(f"@PG\tID:realigner\tPN:realigner\tVN:{cfg.__version__}\tCL:{' '.join(argv if argv is not None else sys.argv)}\n")
 
 
-def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=None):
+class NativeBam:
+    """A BAM file opened through libnpore_b200.so (include/npore_bamio.h): header, per-record columns, flat gathers."""
+
+    COLUMNS = ("ref_id", "pos", "end", "flag", "mapq", "aln_len", "n_cigar", "name_len", "hp", "has_qual")
+
+    def __init__(self, path, n_threads=0):
+        from ._lib import lib
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.npore_bam_open(os.fsencode(path), n_threads, C.byref(h))
+        if rc:
+            raise (FileNotFoundError if rc == -1 else ValueError)(f"{path}: {self._L.npore_io_last_error().decode()}")
+        self._h = h
+        t = C.c_char_p()
+        self._L.npore_bam_header_text(h, C.byref(t))
+        self.text = (t.value or b"").decode()
+        self.refs = []
+        for i in range(self._L.npore_bam_n_refs(h)):
+            name, length = C.c_char_p(), C.c_int64()
+            self._L.npore_bam_ref(h, i, C.byref(name), C.byref(length))
+            self.refs.append((name.value.decode(), int(length.value)))
+        self.n = int(self._L.npore_bam_n_records(h))
+        cols = {k: np.zeros(max(self.n, 1), np.int32) for k in self.COLUMNS}
+        self._L.npore_bam_columns(h, *[cols[k].ctypes.data for k in self.COLUMNS])
+        for k, v in cols.items():
+            setattr(self, k, v[:self.n])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.npore_bam_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def gather(self, sel, n_threads=0, want_qual=True, want_names=True):
+        """Flat arrays of the selected records: dict with seq_ascii, seq_codes, qual_ascii, seq_off, cigar, cig_off, names,
+        name_off (soft clips removed, S/H dropped from the CIGAR; bam.pyx:41-44, 59)."""
+        sel = np.ascontiguousarray(sel, dtype=np.int64)
+        off = lambda col: np.concatenate(([0], np.cumsum(col[sel], dtype=np.int64)))   # noqa: E731
+        o = {"seq_off": off(self.aln_len), "cig_off": off(self.n_cigar), "name_off": off(self.name_len)}
+        o["seq_ascii"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8)
+        o["seq_codes"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8)
+        o["qual_ascii"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8) if want_qual else None
+        o["cigar"] = np.empty(max(int(o["cig_off"][-1]), 1), np.uint32)
+        o["names"] = np.empty(max(int(o["name_off"][-1]), 1), np.uint8) if want_names else None
+        ptr = lambda a: None if a is None else a.ctypes.data   # noqa: E731
+        rc = self._L.npore_bam_gather(self._h, len(sel), ptr(sel) if len(sel) else None, n_threads, ptr(o["seq_ascii"]), ptr(o["seq_codes"]),
+                                      ptr(o["qual_ascii"]), ptr(o["seq_off"]), ptr(o["cigar"]), ptr(o["cig_off"]), ptr(o["names"]), ptr(o["name_off"]))
+        if rc:
+            raise RuntimeError(self._L.npore_io_last_error().decode())
+        return o
+
+
+def format_sam(bam, sel, g, rle, rle_off, n_threads=0):
+    """bam.pyx:83 for the selected records as one bytes-like block (npore_sam_format)."""
+    L = bam._L
+    names = "".join(n for n, _ in bam.refs).encode()
+    rn_off = np.concatenate(([0], np.cumsum([len(n.encode()) for n, _ in bam.refs], dtype=np.int64)))
+    rn = np.frombuffer(names, dtype=np.uint8) if names else np.zeros(1, np.uint8)
+    rle = np.ascontiguousarray(rle, dtype=np.uint32)
+    rle_off = np.ascontiguousarray(rle_off, dtype=np.int64)
+    n = len(sel)
+    cap = int(L.npore_sam_bound(n, g["name_off"].ctypes.data, g["seq_off"].ctypes.data, rle_off.ctypes.data, max([len(x) for x, _ in bam.refs] + [1])))
+    out = np.empty(max(cap, 1), np.uint8)
+    col = lambda a: np.ascontiguousarray(a[sel], dtype=np.int32)   # noqa: E731
+    flag, ref_id, pos, end, mapq, hq, hp = (col(getattr(bam, k)) for k in ("flag", "ref_id", "pos", "end", "mapq", "has_qual", "hp"))
+    qual = g["qual_ascii"] if g["qual_ascii"] is not None else g["seq_ascii"]
+    if g["qual_ascii"] is None:
+        hq = np.zeros_like(hq)
+    got = L.npore_sam_format(n, n_threads, g["names"].ctypes.data, g["name_off"].ctypes.data, flag.ctypes.data, ref_id.ctypes.data,
+                             rn.ctypes.data, rn_off.ctypes.data, pos.ctypes.data, end.ctypes.data, mapq.ctypes.data,
+                             rle.ctypes.data if len(rle) else None, rle_off.ctypes.data, g["seq_ascii"].ctypes.data, qual.ctypes.data,
+                             g["seq_off"].ctypes.data, hq.ctypes.data, hp.ctypes.data, out.ctypes.data, cap)
+    if got < 0:
+        raise RuntimeError(L.npore_io_last_error().decode())
+    return out[:got]
+
+
+def select_reads(bam, regions=None, max_reads=0):
+    """Record indices per region like bam.pyx:26-32: fetch(ctg, start, stop) order, no secondary / supplementary /
+    unmapped reads, at most max_reads in total.  Yields (contig, indices)."""
+    ok = ((bam.flag & (0x4 | 0x100 | 0x800)) == 0) & (bam.ref_id >= 0)
+    names = [n for n, _ in bam.refs]
+    kept = 0
+    for ctg, start, stop in (regions or [(n, 0, l) for n, l in bam.refs]):
+        if ctg not in names:
+            continue
+        sel = np.flatnonzero(ok & (bam.ref_id == names.index(ctg)) & (bam.pos < stop) & (bam.end > start))
+        if max_reads:
+            sel = sel[:max(0, max_reads - kept)]
+        kept += len(sel)
+        if len(sel):
+            yield ctg, sel
+
+
+def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=None, max_batch_ops=64_000_000, n_threads=0,
+                timings=None):
     """realign.py:75-115 without pysam / Pool: header, ingest, GPU realignment, records appended in input order
-    (= coordinate order for a sorted BAM, which is what the header claims)."""
-    from .bam import realign_reads
+    (= coordinate order for a sorted BAM, which is what the header claims).  Returns the number of records written.
+    Flat arrays all the way: native decode -> npore_align_batch (one shared reference slice per batch) -> native SAM text.
+    timings: optional dict that receives seconds per phase (open, gather, gpu, format, write)."""
+    import time
+    tm = timings if timings is not None else {}
+    for k in ("open", "gather", "gpu", "format", "write"):
+        tm.setdefault(k, 0.0)
+    t0 = time.perf_counter()
+    from .bam import _tables
+    from .aln import _engine, _report
+    from .cig import bases_to_int
+    from .engine import NPORE_OUT_NO_EXPANDED, NPORE_OUT_RLE, NPORE_OUT_STANDARDIZE, PackedBatch
     if out_prefix is not None:
         cfg.args.out_prefix = out_prefix
-    _, refs, _ = read_bam(bam_fn)
-    create_header(f"{cfg.args.out_prefix}.sam", refs, argv)
-    return realign_reads(get_read_data(bam_fn, fasta, regions, max_reads), write=True)
+    if not os.path.exists(bam_fn):
+        print(f"\nERROR: BAM file '{bam_fn}' not found.")
+        sys.exit(1)
+    fa = read_fasta(fasta) if isinstance(fasta, str) else fasta
+    bam = NativeBam(bam_fn, n_threads)
+    tm["open"] += time.perf_counter() - t0
+    create_header(f"{cfg.args.out_prefix}.sam", bam.refs, argv)
+    sub, npt = _tables()
+    eng = _engine(sub, npt, 5, 1, 20000, 30)
+    flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED
+    written = 0
+    codes = {}
+    with open(f"{cfg.args.out_prefix}.sam", "ab") as fh:
+        for ctg, sel in select_reads(bam, regions, max_reads):
+            if ctg not in codes:
+                codes = {ctg: bases_to_int(fa[ctg].upper())}            # one contig resident at a time
+            ops = np.cumsum((bam.end[sel] - bam.pos[sel]).astype(np.int64) + bam.aln_len[sel])
+            cut = 0
+            while cut < len(sel):
+                stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
+                part = sel[cut:stop]
+                t0 = time.perf_counter()
+                g = bam.gather(part, n_threads)
+                t1 = time.perf_counter()
+                lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
+                packed = PackedBatch.from_flat_shared(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
+                                                      g["seq_codes"][:int(g["seq_off"][-1])], bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
+                res = eng.align_packed(packed, flags, eng.new_result(packed, flags, pinned=False))
+                _report(res.status[:packed.n], "realign_read")
+                t2 = time.perf_counter()
+                blob = format_sam(bam, part, g, res.rle, res.rle_off[:packed.n + 1], n_threads)
+                t3 = time.perf_counter()
+                fh.write(memoryview(blob))
+                t4 = time.perf_counter()
+                tm["gather"] += t1 - t0; tm["gpu"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += t4 - t3
+                written += len(part)
+                with cfg.counter.get_lock():
+                    cfg.counter.value += len(part)
+                cut = stop
+    bam.close()
+    return written
 
 
 # ------------------------------------------------------------------------------------------------ minimal BAM writer

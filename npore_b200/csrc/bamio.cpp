@@ -1,0 +1,378 @@
+// bamio.cpp -- native BAM ingest (BGZF inflate + record decode) and SAM record formatting; include/npore_bamio.h.
+// Replaces, for the realignment path, what the reference reads through pysam (src/bam.pyx:18-47) and prints per read
+// (src/bam.pyx:81-84).  Formats follow the SAM/BAM specification (section 4: BGZF members with a BC extra field;
+// records `block_size, refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, l_seq, next_refID, next_pos, tlen,
+// read_name, cigar, seq (4-bit =ACMGRSVTWYHKDBN), qual, aux`).
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/npore_bamio.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int io_fail(int code, const std::string &what) { g_err = what; return code; }
+
+template <class F>
+void parallel_for(int64_t n, int n_threads, F &&body)        // body(begin, end) on contiguous slices
+{
+    int t = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    t = (int)std::max<int64_t>(1, std::min<int64_t>(t, n));
+    if (t == 1) { body((int64_t)0, n); return; }
+    std::vector<std::thread> pool;
+    for (int k = 0; k < t; k++) pool.emplace_back([=, &body] { body(n * k / t, n * (k + 1) / t); });
+    for (auto &th : pool) th.join();
+}
+
+inline uint32_t rd32(const uint8_t *p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+inline uint16_t rd16(const uint8_t *p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
+
+struct Rec {                // decoded once at open
+    int64_t off;            // offset of the record's refID field in `data`
+    int32_t ref_id, pos, end, l_seq, n_cigar, n_cigar_kept, lead, trail, hp, name_len;
+    uint16_t flag; uint8_t mapq, has_qual;
+};
+
+}  // namespace
+
+struct npore_bam {
+    std::vector<uint8_t> data;            // the inflated BAM stream
+    std::string text;
+    std::vector<std::string> ref_names;
+    std::vector<int64_t> ref_lens;
+    std::vector<Rec> recs;
+};
+
+namespace {
+
+// value of an integer-typed HP aux tag, 0 if absent (bam.pyx:46)
+int32_t find_hp(const uint8_t *p, const uint8_t *e)
+{
+    while (p + 3 <= e) {
+        const bool hp = p[0] == 'H' && p[1] == 'P';
+        const char t = (char)p[2];
+        p += 3;
+        switch (t) {
+        case 'A': case 'c': case 'C': if (hp && t != 'A' && p < e) return t == 'c' ? (int8_t)p[0] : p[0]; p += 1; break;
+        case 's': case 'S': if (hp && p + 2 <= e) return t == 's' ? (int16_t)rd16(p) : rd16(p); p += 2; break;
+        case 'i': case 'I': if (hp && p + 4 <= e) return (int32_t)rd32(p); p += 4; break;
+        case 'f': p += 4; break;
+        case 'Z': case 'H': while (p < e && *p) p++; p++; break;
+        case 'B': {
+            if (p + 5 > e) return 0;
+            const char st = (char)p[0]; const uint32_t cnt = rd32(p + 1);
+            const int sz = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+            p += 5 + (size_t)cnt * sz; break;
+        }
+        default: return 0;
+        }
+    }
+    return 0;
+}
+
+const uint8_t kNt16[17] = "=ACMGRSVTWYHKDBN";
+
+}  // namespace
+
+extern "C" {
+
+const char *npore_io_last_error(void) { return g_err.c_str(); }
+
+int npore_bam_open(const char *path, int n_threads, npore_bam **out)
+{
+    if (!path || !out) return io_fail(NPORE_IO_ERR_ARG, "null argument");
+    *out = nullptr;
+    FILE *fh = std::fopen(path, "rb");
+    if (!fh) return io_fail(NPORE_IO_ERR_OPEN, std::string("cannot open ") + path);
+    std::fseek(fh, 0, SEEK_END);
+    const long fsz = std::ftell(fh);
+    std::fseek(fh, 0, SEEK_SET);
+    std::vector<uint8_t> file((size_t)std::max<long>(fsz, 0));
+    const size_t got = file.empty() ? 0 : std::fread(file.data(), 1, file.size(), fh);
+    std::fclose(fh);
+    if (got != file.size()) return io_fail(NPORE_IO_ERR_OPEN, std::string("short read on ") + path);
+
+    // ---- BGZF members: 12 fixed bytes, XLEN extra (subfield 'B','C' holds BSIZE = member size - 1), deflate data, CRC32, ISIZE
+    struct Blk { size_t coff, clen, uoff, ulen; uint32_t crc; };
+    std::vector<Blk> blks;
+    size_t p = 0, utotal = 0;
+    while (p < file.size()) {
+        if (p + 18 > file.size() || file[p] != 0x1f || file[p + 1] != 0x8b || file[p + 2] != 8 || !(file[p + 3] & 4))
+            return io_fail(NPORE_IO_ERR_FORMAT, "not a BGZF file (bad member header)");
+        const size_t xlen = rd16(&file[p + 10]);
+        size_t q = p + 12, xe = q + xlen, bsize = 0;
+        if (xe > file.size()) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF header");
+        while (q + 4 <= xe) {
+            const size_t sl = rd16(&file[q + 2]);
+            if (file[q] == 'B' && file[q + 1] == 'C' && sl == 2) bsize = (size_t)rd16(&file[q + 4]) + 1;
+            q += 4 + sl;
+        }
+        if (!bsize || p + bsize > file.size() || bsize < xlen + 20) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF member");
+        Blk b;
+        b.coff = xe; b.clen = bsize - xlen - 20;
+        b.crc = rd32(&file[p + bsize - 8]); b.ulen = rd32(&file[p + bsize - 4]); b.uoff = utotal;
+        utotal += b.ulen;
+        blks.push_back(b);
+        p += bsize;
+    }
+    npore_bam *bam = new npore_bam();
+    bam->data.resize(utotal);
+    std::atomic<int> bad{0};
+    parallel_for((int64_t)blks.size(), n_threads, [&](int64_t lo, int64_t hi) {
+        z_stream zs;
+        for (int64_t k = lo; k < hi; k++) {
+            const Blk &b = blks[(size_t)k];
+            if (!b.ulen) continue;
+            std::memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+            zs.next_in = const_cast<Bytef *>(&file[b.coff]); zs.avail_in = (uInt)b.clen;
+            zs.next_out = &bam->data[b.uoff]; zs.avail_out = (uInt)b.ulen;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), &bam->data[b.uoff], (uInt)b.ulen) != b.crc) { bad = 1; return; }
+        }
+    });
+    if (bad) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "BGZF member failed to inflate (corrupt data or CRC mismatch)"); }
+    std::vector<uint8_t>().swap(file);
+
+    // ---- BAM header
+    const std::vector<uint8_t> &d = bam->data;
+    auto need = [&](size_t at, size_t n) { return at + n <= d.size(); };
+    if (!need(0, 12) || std::memcmp(d.data(), "BAM\1", 4) != 0) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "not a BAM file"); }
+    size_t at = 4;
+    const size_t l_text = rd32(&d[at]); at += 4;
+    if (!need(at, l_text + 4)) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM header"); }
+    bam->text.assign((const char *)&d[at], l_text);
+    bam->text = bam->text.c_str();                    // drop NUL padding
+    at += l_text;
+    const size_t n_ref = rd32(&d[at]); at += 4;
+    for (size_t i = 0; i < n_ref; i++) {
+        if (!need(at, 4)) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM reference list"); }
+        const size_t l_name = rd32(&d[at]); at += 4;
+        if (!need(at, l_name + 4) || !l_name) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM reference list"); }
+        bam->ref_names.emplace_back((const char *)&d[at], l_name - 1); at += l_name;
+        bam->ref_lens.push_back((int64_t)rd32(&d[at])); at += 4;
+    }
+    // ---- record index, then the per-record columns in parallel
+    std::vector<int64_t> offs;
+    while (at + 4 <= d.size()) {
+        const size_t bs = rd32(&d[at]);
+        if (bs < 32 || !need(at + 4, bs)) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM record"); }
+        offs.push_back((int64_t)at + 4);
+        at += 4 + bs;
+    }
+    bam->recs.resize(offs.size());
+    parallel_for((int64_t)offs.size(), n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; k++) {
+            const uint8_t *r = &d[(size_t)offs[(size_t)k]];
+            const size_t bs = rd32(r - 4);
+            Rec &o = bam->recs[(size_t)k];
+            o.off = offs[(size_t)k];
+            o.ref_id = (int32_t)rd32(r); o.pos = (int32_t)rd32(r + 4);
+            o.name_len = r[8] ? r[8] - 1 : 0; o.mapq = r[9];
+            o.n_cigar = rd16(r + 12); o.flag = rd16(r + 14); o.l_seq = (int32_t)rd32(r + 16);
+            const uint8_t *cg = r + 32 + r[8];
+            const uint8_t *sq = cg + 4 * (size_t)o.n_cigar;
+            const uint8_t *ql = sq + ((size_t)o.l_seq + 1) / 2;
+            const uint8_t *aux = ql + o.l_seq, *end = r + bs;
+            if (aux > end) { o.n_cigar = 0; o.l_seq = 0; aux = end; }          // malformed record: treated as empty
+            int64_t span = 0; int kept = 0;
+            for (int c = 0; c < o.n_cigar; c++) {
+                const uint32_t w = rd32(cg + 4 * c), op = w & 15u;
+                if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += w >> 4;
+                if (op != 4 && op != 5) kept++;
+            }
+            o.end = o.pos + (int32_t)span; o.n_cigar_kept = kept;
+            auto opat = [&](int c) { return rd32(cg + 4 * c) & 15u; };
+            auto lnat = [&](int c) { return (int32_t)(rd32(cg + 4 * c) >> 4); };
+            const int nc = o.n_cigar;
+            o.lead = nc && opat(0) == 4 ? lnat(0) : (nc > 1 && opat(0) == 5 && opat(1) == 4 ? lnat(1) : 0);
+            o.trail = nc && opat(nc - 1) == 4 ? lnat(nc - 1) : (nc > 1 && opat(nc - 1) == 5 && opat(nc - 2) == 4 ? lnat(nc - 2) : 0);
+            if (o.lead + o.trail > o.l_seq) { o.lead = std::min(o.lead, o.l_seq); o.trail = o.l_seq - o.lead; }
+            o.has_qual = (o.l_seq > 0 && ql[0] != 0xff) ? 1 : 0;
+            o.hp = find_hp(aux, end);
+        }
+    });
+    *out = bam;
+    return NPORE_IO_OK;
+}
+
+void npore_bam_close(npore_bam *b) { delete b; }
+
+int64_t npore_bam_header_text(const npore_bam *b, const char **text)
+{
+    if (!b) return NPORE_IO_ERR_ARG;
+    if (text) *text = b->text.c_str();
+    return (int64_t)b->text.size();
+}
+
+int32_t npore_bam_n_refs(const npore_bam *b) { return b ? (int32_t)b->ref_names.size() : NPORE_IO_ERR_ARG; }
+
+int npore_bam_ref(const npore_bam *b, int32_t i, const char **name, int64_t *length)
+{
+    if (!b || i < 0 || (size_t)i >= b->ref_names.size()) return io_fail(NPORE_IO_ERR_ARG, "reference index out of range");
+    if (name) *name = b->ref_names[(size_t)i].c_str();
+    if (length) *length = b->ref_lens[(size_t)i];
+    return NPORE_IO_OK;
+}
+
+int64_t npore_bam_n_records(const npore_bam *b) { return b ? (int64_t)b->recs.size() : NPORE_IO_ERR_ARG; }
+
+int npore_bam_columns(const npore_bam *b, int32_t *ref_id, int32_t *pos, int32_t *end, int32_t *flag, int32_t *mapq,
+                      int32_t *aln_len, int32_t *n_cigar, int32_t *name_len, int32_t *hp, int32_t *has_qual)
+{
+    if (!b) return io_fail(NPORE_IO_ERR_ARG, "null handle");
+    for (size_t k = 0; k < b->recs.size(); k++) {
+        const Rec &r = b->recs[k];
+        if (ref_id) ref_id[k] = r.ref_id;
+        if (pos) pos[k] = r.pos;
+        if (end) end[k] = r.end;
+        if (flag) flag[k] = r.flag;
+        if (mapq) mapq[k] = r.mapq;
+        if (aln_len) aln_len[k] = r.l_seq - r.lead - r.trail;
+        if (n_cigar) n_cigar[k] = r.n_cigar_kept;
+        if (name_len) name_len[k] = r.name_len;
+        if (hp) hp[k] = r.hp;
+        if (has_qual) has_qual[k] = r.has_qual;
+    }
+    return NPORE_IO_OK;
+}
+
+int npore_bam_gather(const npore_bam *b, int64_t n_sel, const int64_t *sel, int n_threads,
+                     uint8_t *seq_ascii, uint8_t *seq_codes, uint8_t *qual_ascii, const int64_t *seq_off,
+                     uint32_t *cigar, const int64_t *cig_off, uint8_t *names, const int64_t *name_off)
+{
+    if (!b || n_sel < 0 || (n_sel && !sel)) return io_fail(NPORE_IO_ERR_ARG, "null argument");
+    if (((seq_ascii || seq_codes || qual_ascii) && !seq_off) || (cigar && !cig_off) || (names && !name_off))
+        return io_fail(NPORE_IO_ERR_ARG, "offsets missing");
+    for (int64_t k = 0; k < n_sel; k++)
+        if (sel[k] < 0 || (size_t)sel[k] >= b->recs.size()) return io_fail(NPORE_IO_ERR_ARG, "record index out of range");
+    uint8_t code_of[16];
+    for (int c = 0; c < 16; c++) code_of[c] = kNt16[c] == 'A' ? 1 : kNt16[c] == 'C' ? 2 : kNt16[c] == 'G' ? 3 : kNt16[c] == 'T' ? 4 : 0;
+    std::atomic<int> bad{0};
+    parallel_for(n_sel, n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; k++) {
+            const Rec &r = b->recs[(size_t)sel[k]];
+            const uint8_t *rec = &b->data[(size_t)r.off];
+            const uint8_t *cg = rec + 32 + rec[8];
+            const uint8_t *sq = cg + 4 * (size_t)r.n_cigar;
+            const uint8_t *ql = sq + ((size_t)r.l_seq + 1) / 2;
+            const int n = r.l_seq - r.lead - r.trail;
+            if (seq_off && seq_off[k + 1] - seq_off[k] != n) { bad = 1; continue; }
+            if (cig_off && cig_off[k + 1] - cig_off[k] != r.n_cigar_kept) { bad = 1; continue; }
+            if (name_off && name_off[k + 1] - name_off[k] != r.name_len) { bad = 1; continue; }
+            if (seq_ascii || seq_codes) {
+                uint8_t *a = seq_ascii ? seq_ascii + seq_off[k] : nullptr, *c = seq_codes ? seq_codes + seq_off[k] : nullptr;
+                for (int t = 0; t < n; t++) {
+                    const int q = r.lead + t;
+                    const int nib = (q & 1) ? (sq[q >> 1] & 15) : (sq[q >> 1] >> 4);
+                    if (a) a[t] = kNt16[nib];
+                    if (c) c[t] = code_of[nib];
+                }
+            }
+            if (qual_ascii && r.has_qual) {
+                uint8_t *o = qual_ascii + seq_off[k];
+                for (int t = 0; t < n; t++) o[t] = (uint8_t)(ql[r.lead + t] + 33);
+            }
+            if (cigar) {
+                uint32_t *o = cigar + cig_off[k];
+                for (int c = 0; c < r.n_cigar; c++) {
+                    const uint32_t w = rd32(cg + 4 * c), op = w & 15u;
+                    if (op != 4 && op != 5) *o++ = w;
+                }
+            }
+            if (names) std::memcpy(names + name_off[k], rec + 32, (size_t)r.name_len);
+        }
+    });
+    if (bad) return io_fail(NPORE_IO_ERR_ARG, "offset arrays do not match the selected records");
+    return NPORE_IO_OK;
+}
+
+static inline int dec_len(uint32_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n; }
+static inline uint8_t *put_dec(uint8_t *o, int64_t v)
+{
+    if (v < 0) { *o++ = '-'; v = -v; }
+    char tmp[24]; int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *o++ = (uint8_t)tmp[--n];
+    return o;
+}
+
+int64_t npore_sam_bound(int64_t n, const int64_t *name_off, const int64_t *seq_off, const int64_t *rle_off, int64_t max_ref_name)
+{
+    if (n < 0 || (n && (!name_off || !seq_off || !rle_off))) return NPORE_IO_ERR_ARG;
+    if (!n) return 0;
+    // per record: 11 tabs + newline + numeric fields (flag 5, pos 11, mapq 3, tlen 11, hp 11) + "*", "0", "HP:i:" + slack
+    return (name_off[n] - name_off[0]) + 2 * (seq_off[n] - seq_off[0]) + 10 * (rle_off[n] - rle_off[0]) + n * (72 + max_ref_name);
+}
+
+int64_t npore_sam_format(int64_t n, int n_threads,
+                         const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
+                         const uint8_t *ref_names, const int64_t *ref_name_off,
+                         const int32_t *pos, const int32_t *end, const int32_t *mapq,
+                         const uint32_t *rle, const int64_t *rle_off,
+                         const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
+                         const int32_t *hp, uint8_t *out, int64_t out_capacity)
+{
+    if (n < 0) return io_fail(NPORE_IO_ERR_ARG, "negative count");
+    if (!n) return 0;
+    if (!names || !name_off || !flag || !ref_id || !ref_names || !ref_name_off || !pos || !end || !mapq || !rle_off || !seq_off ||
+        !has_qual || !hp || !out)
+        return io_fail(NPORE_IO_ERR_ARG, "null argument");
+    static const char kOps[] = "MIDNSHP=XB??????";
+    std::vector<int64_t> at((size_t)n + 1, 0);
+    // pass 1: exact record lengths
+    parallel_for(n, n_threads, [&](int64_t lo, int64_t hi) {
+        uint8_t tmp[32];
+        for (int64_t k = lo; k < hi; k++) {
+            int64_t len = 12;                                         // 11 tabs + '\n'
+            len += name_off[k + 1] - name_off[k];
+            len += put_dec(tmp, flag[k]) - tmp;
+            len += ref_name_off[ref_id[k] + 1] - ref_name_off[ref_id[k]];
+            len += put_dec(tmp, (int64_t)pos[k] + 1) - tmp;
+            len += put_dec(tmp, mapq[k]) - tmp;
+            for (int64_t g = rle_off[k]; g < rle_off[k + 1]; g++) len += dec_len(rle[g] >> 4) + 1;
+            len += 2;                                                 // "*" and "0"
+            len += put_dec(tmp, (int64_t)end[k] - pos[k]) - tmp;
+            const int64_t sl = seq_off[k + 1] - seq_off[k];
+            len += sl + ((has_qual[k] && sl) ? sl : 1);
+            len += 5 + (put_dec(tmp, hp[k]) - tmp);
+            at[(size_t)k + 1] = len;
+        }
+    });
+    for (int64_t k = 0; k < n; k++) at[(size_t)k + 1] += at[(size_t)k];
+    if (at[(size_t)n] > out_capacity) return io_fail(NPORE_IO_ERR_ARG, "output buffer too small (use npore_sam_bound)");
+    // pass 2: write
+    parallel_for(n, n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; k++) {
+            uint8_t *o = out + at[(size_t)k];
+            const int64_t nl = name_off[k + 1] - name_off[k];
+            std::memcpy(o, names + name_off[k], (size_t)nl); o += nl; *o++ = '\t';
+            o = put_dec(o, flag[k]); *o++ = '\t';
+            const int64_t rl = ref_name_off[ref_id[k] + 1] - ref_name_off[ref_id[k]];
+            std::memcpy(o, ref_names + ref_name_off[ref_id[k]], (size_t)rl); o += rl; *o++ = '\t';
+            o = put_dec(o, (int64_t)pos[k] + 1); *o++ = '\t';
+            o = put_dec(o, mapq[k]); *o++ = '\t';
+            for (int64_t g = rle_off[k]; g < rle_off[k + 1]; g++) { o = put_dec(o, rle[g] >> 4); *o++ = (uint8_t)kOps[rle[g] & 15u]; }
+            *o++ = '\t'; *o++ = '*'; *o++ = '\t'; *o++ = '0'; *o++ = '\t';
+            o = put_dec(o, (int64_t)end[k] - pos[k]); *o++ = '\t';
+            const int64_t sl = seq_off[k + 1] - seq_off[k];
+            std::memcpy(o, seq_ascii + seq_off[k], (size_t)sl); o += sl; *o++ = '\t';
+            if (has_qual[k] && sl) { std::memcpy(o, qual_ascii + seq_off[k], (size_t)sl); o += sl; } else *o++ = '*';
+            *o++ = '\t';
+            std::memcpy(o, "HP:i:", 5); o += 5;
+            o = put_dec(o, hp[k]); *o++ = '\n';
+        }
+    });
+    return at[(size_t)n];
+}
+
+}  // extern "C"

@@ -193,6 +193,17 @@ class PackedBatch:
         return self
 
     @classmethod
+    def from_flat_shared(cls, ref_codes, ref_start, ref_len, seq_codes, seq_len, cigar_rle, cigar_off):
+        """Like from_flat, but every item addresses a window (ref_start, ref_len) of ONE shared reference buffer (a contig
+        slice uploaded once instead of one copy per read)."""
+        self = cls.from_flat(np.zeros(0, np.uint8), ref_len, seq_codes, seq_len, cigar_rle, cigar_off)
+        self.ref_codes = np.ascontiguousarray(ref_codes, dtype=np.uint8) if len(ref_codes) else np.zeros(1, np.uint8)
+        self.ref_start = np.ascontiguousarray(ref_start, dtype=np.int64)
+        self.ref_total = int(len(ref_codes))
+        self.total_ops = int(self.ref_len.astype(np.int64).sum()) + self.seq_total
+        return self
+
+    @classmethod
     def from_strings(cls, refs, seqs, cigars):
         """refs / seqs: base strings; cigars: CIGAR texts (all run-length or all expanded)."""
         rc, rl = bases_to_int_batch(refs)

@@ -54,6 +54,53 @@ def test_soft_clips_are_stripped(tmp_path):
     assert t == ("x", 0, "c", 2, 9, "2S4=1S", 6, "GTAC", "".join(chr(33 + q) for q in (3, 4, 5, 6)), "GTAC", 2)
 
 
+def test_native_reader_matches_python_reader(golden, tmp_path):
+    """libnpore_b200.so's BAM ingest (include/npore_bamio.h; host code, no GPU needed) == the pure-Python decode, incl. soft /
+    hard clips, missing qualities, lower-case and IUPAC bases, HP tags of several integer types, filtered records."""
+    from npore_b200 import cig
+    bam, fasta, reads, _ = _fixture(golden, tmp_path)
+    extra = tmp_path / "x.bam"
+    recs = [{"name": "clip", "flag": 16, "ref_id": 0, "pos": 2, "mapq": 9, "cigar": [(3, "H"), (2, "S"), (4, "="), (1, "I"), (2, "D"), (3, "X"), (1, "S")],
+             "seq": "ttGTACRacng", "qual": bytes(range(1, 12)), "tags": {"HP": 2}},
+            {"name": "noq", "flag": 0, "ref_id": 0, "pos": 7, "mapq": 60, "cigar": [(5, "M")], "seq": "ACGTN", "qual": None},
+            {"name": "sec", "flag": 0x100, "ref_id": 0, "pos": 8, "mapq": 1, "cigar": [(2, "M")], "seq": "AC", "qual": None},
+            {"name": "other", "flag": 0, "ref_id": 1, "pos": 0, "mapq": 3, "cigar": [(4, "S"), (2, "M")], "seq": "ACGTAC", "qual": bytes(6)}]
+    bamio.write_bam(str(extra), "@HD\tVN:1.6\n", [("c", 30), ("d", 9)], recs)
+    fa2 = {"c": "ACGTACGTACGTACGTACGTACGTACGTAC", "d": "ACGTACGTA"}
+    for path, fa in ((bam, bamio.read_fasta(fasta)), (str(extra), fa2)):
+        nb = bamio.NativeBam(path, n_threads=3)
+        text, refs, _ = bamio.read_bam(path)
+        assert nb.refs == refs and nb.text == text
+        want = list(bamio.get_read_data(path, fa))
+        sels = list(bamio.select_reads(nb))
+        sel = np.concatenate([s for _, s in sels])
+        assert len(sel) == len(want)
+        g = nb.gather(sel, n_threads=2)
+        for k, w in enumerate(want):
+            cut = lambda a, o: a[g[o][k]:g[o][k + 1]]   # noqa: E731
+            assert cut(g["names"], "name_off").tobytes().decode() == w[0]
+            assert (nb.flag[sel[k]], nb.refs[nb.ref_id[sel[k]]][0], nb.pos[sel[k]], nb.mapq[sel[k]], nb.end[sel[k]], nb.hp[sel[k]]) == (w[1], w[2], w[3], w[4], w[6], w[10])
+            assert cut(g["seq_ascii"], "seq_off").tobytes().decode() == w[7]
+            assert np.array_equal(cut(g["seq_codes"], "seq_off"), cig.bases_to_int(w[7]))
+            assert (cut(g["qual_ascii"], "seq_off").tobytes().decode() if nb.has_qual[sel[k]] else "*") == w[8]
+            assert "".join(f"{int(x) >> 4}{'MIDNSHP=XB'[int(x) & 15]}" for x in cut(g["cigar"], "cig_off")) == re.sub(r"\d+[SH]", "", w[5])
+        # SAM text of the batch formatter == bam.sam_record, with the (clip-free) input CIGARs standing in for results
+        from npore_b200.bam import sam_record
+        from npore_b200.engine import cigars_to_rle_batch
+        kept = [re.sub(r"\d+[SH]", "", w[5]) for w in want]
+        words, off = cigars_to_rle_batch(kept)
+        blob = bamio.format_sam(nb, sel, g, words, off, n_threads=2).tobytes().decode()
+        assert blob == "".join(sam_record(w, c) + "\n" for w, c in zip(want, kept))
+        assert len(list(bamio.select_reads(nb, max_reads=1))[0][1]) == 1
+        nb.close()
+    with pytest.raises(FileNotFoundError):
+        bamio.NativeBam(str(tmp_path / "missing.bam"))
+    bad = tmp_path / "bad.bam"
+    bad.write_bytes(open(bam, "rb").read()[:200])
+    with pytest.raises(ValueError):
+        bamio.NativeBam(str(bad))
+
+
 def test_header(tmp_path):
     out = tmp_path / "d" / "o.sam"
     bamio.create_header(str(out), [("chr1", 100), ("chr2", 50)], argv=["realign.py", "--bam", "x"])
@@ -78,8 +125,16 @@ def test_realign_bam_end_to_end(golden, tables, tmp_path):
     bam, fasta, reads, g = _fixture(golden, tmp_path)
     cfg.args.sub_scores, cfg.args.np_scores = tables
     cfg.args.max_n, cfg.args.max_l = 6, 100
-    lines = bamio.realign_bam(bam, fasta, out_prefix=str(tmp_path / "out"), argv=["realign.py"])
+    n = bamio.realign_bam(bam, fasta, out_prefix=str(tmp_path / "out"), argv=["realign.py"])
     want = {l.split("\t")[0]: l for l in g["expected_sam"]}
-    assert lines == [want[r[0]] for r in reads]
-    body = [l for l in open(str(tmp_path / "out.sam")).read().splitlines() if not l.startswith("@")]
-    assert body == lines
+    text = open(str(tmp_path / "out.sam")).read().splitlines()
+    assert n == len(reads) and text[0] == "@HD\tVN:1.6\tSO:coordinate" and text[1] == "@SQ\tSN:ref\tLN:1001"
+    assert [l for l in text if not l.startswith("@")] == [want[r[0]] for r in reads]
+    # the tuple API (bam.pyx:18-89 call for call) writes the same records
+    from npore_b200 import bam as nbam
+    cfg.args.out_prefix = str(tmp_path / "out2")
+    assert nbam.realign_reads(bamio.get_read_data(bam, fasta), write=False) == [want[r[0]] for r in reads]
+    # several GPU batches and a region restriction
+    n2 = bamio.realign_bam(bam, fasta, out_prefix=str(tmp_path / "out3"), argv=["x"], max_batch_ops=1500, regions=[("ref", 0, reads[3][6])])
+    body3 = [l for l in open(str(tmp_path / "out3.sam")).read().splitlines() if not l.startswith("@")]
+    assert n2 == len(body3) and body3 == [want[r[0]] for r in reads if r[3] < reads[3][6]]

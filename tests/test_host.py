@@ -16,13 +16,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_declared_symbol():
-    """include/npore_b200.h <-> libnpore_b200.so: every declared entry point is exported (and listed in _lib.EXPORTS)."""
-    hdr = open(os.path.join(ROOT, "include", "npore_b200.h")).read()
-    declared = set(re.findall(r"\b(npore_[a-z_0-9]+)\s*\(", hdr))
-    assert declared == set(_lib.EXPORTS)
+    """include/*.h <-> libnpore_b200.so: every declared entry point is exported (and listed in _lib.EXPORTS / IO_EXPORTS)."""
     L = ctypes.CDLL(_lib.LIB_PATH)
-    for name in declared:
-        assert hasattr(L, name), name
+    for header, listed in (("npore_b200.h", _lib.EXPORTS), ("npore_bamio.h", _lib.IO_EXPORTS)):
+        hdr = open(os.path.join(ROOT, "include", header)).read()
+        declared = set(re.findall(r"\b(npore_[a-z_0-9]+)\s*\(", hdr))
+        assert declared == set(listed), header
+        for name in declared:
+            assert hasattr(L, name), name
+    assert sorted(os.listdir(os.path.join(ROOT, "include"))) == ["npore_b200.h", "npore_bamio.h"]
     assert b"sm_100a" in _lib.lib().npore_version()
 
 
