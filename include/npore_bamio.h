@@ -4,7 +4,8 @@
  * These entry points replace, for this path only, what the reference gets from pysam / htslib (a compiled
  * third-party dependency, not part of the TimD1/nPoRe tree):
  *
- *   npore_bam_open / _columns / _gather  <- pysam.AlignmentFile(bam).fetch(...) and the per-read attribute reads of
+ *   npore_bam_open / _advance / _columns / _gather
+ *                                        <- pysam.AlignmentFile(bam).fetch(...) and the per-read attribute reads of
  *                                           src/bam.pyx:18-47 get_read_data(): flag, reference_start, reference_length,
  *                                           mapping_quality, cigar, query_alignment_sequence / _qualities (soft clips
  *                                           removed), HP tag.  BGZF members are inflated on n_threads host threads.
@@ -33,15 +34,19 @@ typedef struct npore_bam npore_bam;
 
 const char *npore_io_last_error(void);
 
-/* read the whole file, inflate its BGZF blocks on n_threads threads (<= 0: all cores), index the records */
+/* open the file and read the BAM header (text + reference list); n_threads (<= 0: all cores) inflate BGZF members */
 int      npore_bam_open(const char *path, int n_threads, npore_bam **out);
+/* load the next window of records: members are inflated until at least max_bytes of record data are available
+ * (<= 0: the rest of the file); records straddling the window end are carried over.  Returns the number of records in
+ * the window (0 at end of file, negative on error).  _n_records / _columns / _gather refer to the current window. */
+int64_t  npore_bam_advance(npore_bam *b, int64_t max_bytes);
 void     npore_bam_close(npore_bam *b);
 int64_t  npore_bam_header_text(const npore_bam *b, const char **text);          /* returns the text length */
 int32_t  npore_bam_n_refs(const npore_bam *b);
 int      npore_bam_ref(const npore_bam *b, int32_t i, const char **name, int64_t *length);
 int64_t  npore_bam_n_records(const npore_bam *b);
 
-/* one value per record, file order.  end = pos + reference span of the CIGAR (M D N = X); aln_len = SEQ length without
+/* one value per record of the current window, file order.  end = pos + reference span of the CIGAR (M D N = X); aln_len = SEQ length without
  * the soft-clipped ends (pysam query_alignment_sequence); n_cigar = CIGAR words once S and H are dropped (bam.pyx:59);
  * hp = value of the HP tag or 0 (bam.pyx:46); has_qual = 0 when QUAL is stored as 0xff.  Any pointer may be NULL. */
 int      npore_bam_columns(const npore_bam *b, int32_t *ref_id, int32_t *pos, int32_t *end, int32_t *flag, int32_t *mapq,

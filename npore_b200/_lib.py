@@ -49,7 +49,7 @@ class PileupBatch(C.Structure):
 EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_set_stream", "npore_count_chunks", "npore_upload", "npore_run", "npore_download",
            "npore_align_batch", "npore_get_np_info", "npore_get_np_info_batch", "npore_confusion_batch", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
 
-IO_EXPORTS = ["npore_io_last_error", "npore_bam_open", "npore_bam_close", "npore_bam_header_text", "npore_bam_n_refs", "npore_bam_ref",
+IO_EXPORTS = ["npore_io_last_error", "npore_bam_open", "npore_bam_advance", "npore_bam_close", "npore_bam_header_text", "npore_bam_n_refs", "npore_bam_ref",
               "npore_bam_n_records", "npore_bam_columns", "npore_bam_gather", "npore_sam_bound", "npore_sam_format"]
 
 _lib = None
@@ -86,6 +86,8 @@ def lib():
         vp = C.c_void_p
         L.npore_io_last_error.restype = C.c_char_p
         L.npore_bam_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.npore_bam_advance.argtypes = [vp, C.c_int64]
+        L.npore_bam_advance.restype = C.c_int64
         L.npore_bam_close.argtypes = [vp]
         L.npore_bam_close.restype = None
         L.npore_bam_header_text.argtypes = [vp, C.POINTER(C.c_char_p)]

@@ -161,7 +161,9 @@ class NativeBam:
 
     COLUMNS = ("ref_id", "pos", "end", "flag", "mapq", "aln_len", "n_cigar", "name_len", "hp", "has_qual")
 
-    def __init__(self, path, n_threads=0):
+    def __init__(self, path, n_threads=0, window_bytes=0):
+        """window_bytes == 0: the whole file is loaded now.  window_bytes > 0: nothing is loaded yet; every advance() call
+        loads the next ~window_bytes of (inflated) records, so files larger than memory stream through."""
         from ._lib import lib
         self._L = lib()
         h = C.c_void_p()
@@ -177,11 +179,24 @@ class NativeBam:
             name, length = C.c_char_p(), C.c_int64()
             self._L.npore_bam_ref(h, i, C.byref(name), C.byref(length))
             self.refs.append((name.value.decode(), int(length.value)))
-        self.n = int(self._L.npore_bam_n_records(h))
-        cols = {k: np.zeros(max(self.n, 1), np.int32) for k in self.COLUMNS}
-        self._L.npore_bam_columns(h, *[cols[k].ctypes.data for k in self.COLUMNS])
+        self.window_bytes = int(window_bytes)
+        self.n = 0
+        for k in self.COLUMNS:
+            setattr(self, k, np.zeros(0, np.int32))
+        if not self.window_bytes:
+            self.advance()
+
+    def advance(self):
+        """Load the next window; returns the number of records in it (0 at end of file)."""
+        n = int(self._L.npore_bam_advance(self._h, self.window_bytes))
+        if n < 0:
+            raise ValueError(self._L.npore_io_last_error().decode())
+        self.n = n
+        cols = {k: np.zeros(max(n, 1), np.int32) for k in self.COLUMNS}
+        self._L.npore_bam_columns(self._h, *[cols[k].ctypes.data for k in self.COLUMNS])
         for k, v in cols.items():
-            setattr(self, k, v[:self.n])
+            setattr(self, k, v[:n])
+        return n
 
     def close(self):
         if getattr(self, "_h", None):
@@ -209,19 +224,21 @@ class NativeBam:
         return o
 
 
-def format_sam(bam, sel, g, rle, rle_off, n_threads=0):
-    """bam.pyx:83 for the selected records as one bytes-like block (npore_sam_format)."""
+def format_sam(bam, sel, g, rle, rle_off, n_threads=0, cols=None):
+    """bam.pyx:83 for the selected records as one bytes-like block (npore_sam_format).  cols: the records' column values
+    taken earlier (dict of int32 arrays: flag ref_id pos end mapq has_qual hp) when the reader has moved on since."""
     L = bam._L
     names = "".join(n for n, _ in bam.refs).encode()
     rn_off = np.concatenate(([0], np.cumsum([len(n.encode()) for n, _ in bam.refs], dtype=np.int64)))
     rn = np.frombuffer(names, dtype=np.uint8) if names else np.zeros(1, np.uint8)
     rle = np.ascontiguousarray(rle, dtype=np.uint32)
     rle_off = np.ascontiguousarray(rle_off, dtype=np.int64)
-    n = len(sel)
+    if cols is None:
+        cols = take_columns(bam, sel)
+    n = len(cols["flag"])
     cap = int(L.npore_sam_bound(n, g["name_off"].ctypes.data, g["seq_off"].ctypes.data, rle_off.ctypes.data, max([len(x) for x, _ in bam.refs] + [1])))
     out = np.empty(max(cap, 1), np.uint8)
-    col = lambda a: np.ascontiguousarray(a[sel], dtype=np.int32)   # noqa: E731
-    flag, ref_id, pos, end, mapq, hq, hp = (col(getattr(bam, k)) for k in ("flag", "ref_id", "pos", "end", "mapq", "has_qual", "hp"))
+    flag, ref_id, pos, end, mapq, hq, hp = (cols[k] for k in ("flag", "ref_id", "pos", "end", "mapq", "has_qual", "hp"))
     qual = g["qual_ascii"] if g["qual_ascii"] is not None else g["seq_ascii"]
     if g["qual_ascii"] is None:
         hq = np.zeros_like(hq)
@@ -232,6 +249,10 @@ def format_sam(bam, sel, g, rle, rle_off, n_threads=0):
     if got < 0:
         raise RuntimeError(L.npore_io_last_error().decode())
     return out[:got]
+
+
+def take_columns(bam, sel):
+    return {k: np.ascontiguousarray(getattr(bam, k)[sel], dtype=np.int32) for k in ("flag", "ref_id", "pos", "end", "mapq", "has_qual", "hp")}
 
 
 def select_reads(bam, regions=None, max_reads=0):
@@ -251,62 +272,124 @@ def select_reads(bam, regions=None, max_reads=0):
             yield ctg, sel
 
 
+_PIPES = {}
+
+
+def _pipeline(sub, npt, n_inflight):
+    """Cached PipelinedRealigner for the current cfg / tables (same idea as aln._engine)."""
+    from .engine import PipelinedRealigner
+    key = (np.asarray(sub, np.float32).tobytes(), hash(np.asarray(npt, np.float32).tobytes()), int(cfg.args.max_n), int(cfg.args.max_l),
+           int(getattr(cfg.args, "device", 0) or 0), n_inflight)
+    p = _PIPES.get(key)
+    if p is None:
+        for old in list(_PIPES):
+            _PIPES.pop(old).close()
+        p = _PIPES[key] = PipelinedRealigner(sub, npt, n_inflight=n_inflight, max_n=int(cfg.args.max_n), max_l=int(cfg.args.max_l),
+                                             device=int(getattr(cfg.args, "device", 0) or 0))
+    return p
+
+
 def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=None, max_batch_ops=64_000_000, n_threads=0,
-                timings=None):
+                timings=None, window_bytes=64 << 20, n_inflight=2):
     """realign.py:75-115 without pysam / Pool: header, ingest, GPU realignment, records appended in input order
     (= coordinate order for a sorted BAM, which is what the header claims).  Returns the number of records written.
-    Flat arrays all the way: native decode -> npore_align_batch (one shared reference slice per batch) -> native SAM text.
-    timings: optional dict that receives seconds per phase (open, gather, gpu, format, write)."""
+    Flat arrays all the way, as a pipeline: the reader streams the file in windows of ~window_bytes of inflated records
+    (native, multi-threaded) and gathers batch k+1 while batch k is on the GPU (n_inflight contexts) and a third thread
+    formats (native) and writes batch k-1.  One shared reference slice is uploaded per batch.
+    timings: optional dict that receives host seconds per phase (open, gather, gpu_wait, format, write)."""
+    import queue
+    import threading
     import time
-    tm = timings if timings is not None else {}
-    for k in ("open", "gather", "gpu", "format", "write"):
-        tm.setdefault(k, 0.0)
-    t0 = time.perf_counter()
     from .bam import _tables
-    from .aln import _engine, _report
+    from .aln import _report
     from .cig import bases_to_int
     from .engine import NPORE_OUT_NO_EXPANDED, NPORE_OUT_RLE, NPORE_OUT_STANDARDIZE, PackedBatch
+    tm = timings if timings is not None else {}
+    for k in ("open", "gather", "gpu_wait", "format", "write"):
+        tm.setdefault(k, 0.0)
+    t0 = time.perf_counter()
     if out_prefix is not None:
         cfg.args.out_prefix = out_prefix
     if not os.path.exists(bam_fn):
         print(f"\nERROR: BAM file '{bam_fn}' not found.")
         sys.exit(1)
     fa = read_fasta(fasta) if isinstance(fasta, str) else fasta
-    bam = NativeBam(bam_fn, n_threads)
-    tm["open"] += time.perf_counter() - t0
+    # several regions are served region by region (bam.pyx:27-28), which needs the whole file at hand
+    bam = NativeBam(bam_fn, n_threads, window_bytes=window_bytes if not (regions and len(regions) > 1) else 0)
+    streaming = bam.window_bytes > 0
     create_header(f"{cfg.args.out_prefix}.sam", bam.refs, argv)
     sub, npt = _tables()
-    eng = _engine(sub, npt, 5, 1, 20000, 30)
+    pipe = _pipeline(sub, npt, n_inflight)
     flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED
-    written = 0
     codes = {}
-    with open(f"{cfg.args.out_prefix}.sam", "ab") as fh:
-        for ctg, sel in select_reads(bam, regions, max_reads):
-            if ctg not in codes:
-                codes = {ctg: bases_to_int(fa[ctg].upper())}            # one contig resident at a time
-            ops = np.cumsum((bam.end[sel] - bam.pos[sel]).astype(np.int64) + bam.aln_len[sel])
-            cut = 0
-            while cut < len(sel):
-                stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
-                part = sel[cut:stop]
-                t0 = time.perf_counter()
-                g = bam.gather(part, n_threads)
+    tm["open"] += time.perf_counter() - t0
+    # stage 3 (own thread): wait for batch k, format its records, append them to the SAM -- in submit order
+    pending = queue.Queue(maxsize=n_inflight + 1)
+    state = {"written": 0, "error": None}
+
+    def retire_loop():
+        with open(f"{cfg.args.out_prefix}.sam", "ab") as fh:
+            while True:
+                item = pending.get()
+                if item is None:
+                    return
+                if state["error"] is not None:
+                    continue                              # keep draining so that the producer never blocks
+                try:
+                    fut, cols, g, n = item
+                    t1 = time.perf_counter()
+                    res, _ = fut.result()
+                    t2 = time.perf_counter()
+                    _report(res.status[:n], "realign_read")
+                    blob = format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols)
+                    t3 = time.perf_counter()
+                    fh.write(memoryview(blob))
+                    tm["gpu_wait"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += time.perf_counter() - t3
+                    state["written"] += n
+                    with cfg.counter.get_lock():
+                        cfg.counter.value += n
+                except Exception as e:                    # noqa: BLE001
+                    state["error"] = e
+
+    retire = threading.Thread(target=retire_loop, daemon=True)
+    retire.start()
+    try:
+        kept = 0
+        while True:
+            if streaming:
                 t1 = time.perf_counter()
-                lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
-                packed = PackedBatch.from_flat_shared(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
-                                                      g["seq_codes"][:int(g["seq_off"][-1])], bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
-                res = eng.align_packed(packed, flags, eng.new_result(packed, flags, pinned=False))
-                _report(res.status[:packed.n], "realign_read")
-                t2 = time.perf_counter()
-                blob = format_sam(bam, part, g, res.rle, res.rle_off[:packed.n + 1], n_threads)
-                t3 = time.perf_counter()
-                fh.write(memoryview(blob))
-                t4 = time.perf_counter()
-                tm["gather"] += t1 - t0; tm["gpu"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += t4 - t3
-                written += len(part)
-                with cfg.counter.get_lock():
-                    cfg.counter.value += len(part)
-                cut = stop
+                more = bam.advance()
+                tm["open"] += time.perf_counter() - t1
+                if not more:
+                    break
+            for ctg, sel in select_reads(bam, regions, (max_reads - kept) if max_reads else 0):
+                kept += len(sel)
+                if ctg not in codes:
+                    codes = {ctg: bases_to_int(fa[ctg].upper())}            # one contig resident at a time
+                ops = np.cumsum((bam.end[sel] - bam.pos[sel]).astype(np.int64) + bam.aln_len[sel])
+                cut = 0
+                while cut < len(sel) and state["error"] is None:
+                    stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
+                    part = sel[cut:stop]
+                    t1 = time.perf_counter()
+                    g = bam.gather(part, n_threads)
+                    lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
+                    packed = PackedBatch.from_flat_shared(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
+                                                          g["seq_codes"][:int(g["seq_off"][-1])], bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
+                    item = (pipe.submit(packed, flags), take_columns(bam, part), g, len(part))
+                    tm["gather"] += time.perf_counter() - t1
+                    pending.put(item)                                        # blocks while n_inflight + 1 batches are unfinished
+                    cut = stop
+                if max_reads and kept >= max_reads:
+                    break
+            if not streaming or (max_reads and kept >= max_reads) or state["error"] is not None:
+                break
+    finally:
+        pending.put(None)
+        retire.join()
+    if state["error"] is not None:
+        raise state["error"]
+    written = state["written"]
     bam.close()
     return written
 

@@ -44,11 +44,16 @@ struct Rec {                // decoded once at open
 }  // namespace
 
 struct npore_bam {
-    std::vector<uint8_t> data;            // the inflated BAM stream
+    FILE *fh = nullptr;
+    bool eof = false;
+    int n_threads = 0;
+    std::vector<uint8_t> data;            // inflated BAM stream of the current window (starts with the bytes carried over)
+    size_t head = 0;                      // first byte of `data` not yet consumed (header / complete records before it)
     std::string text;
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
-    std::vector<Rec> recs;
+    std::vector<Rec> recs;                // records of the current window
+    ~npore_bam() { if (fh) std::fclose(fh); }
 };
 
 namespace {
@@ -86,89 +91,129 @@ extern "C" {
 
 const char *npore_io_last_error(void) { return g_err.c_str(); }
 
+// Append the next BGZF members of the file to b->data until at least `want` more inflated bytes are there (or EOF).
+// Member layout: 12 fixed bytes, XLEN extra (subfield 'B','C' holds BSIZE = member size - 1), deflate data, CRC32, ISIZE.
+static int load_blocks(npore_bam *b, size_t want)
+{
+    struct Blk { size_t coff, clen, uoff, ulen; uint32_t crc; };
+    std::vector<uint8_t> cbuf;
+    std::vector<Blk> blks;
+    size_t added = 0;
+    const size_t base = b->data.size();
+    while (!b->eof && added < want) {
+        uint8_t hd[12];
+        const size_t got = std::fread(hd, 1, 12, b->fh);
+        if (got == 0) { b->eof = true; break; }
+        if (got != 12 || hd[0] != 0x1f || hd[1] != 0x8b || hd[2] != 8 || !(hd[3] & 4))
+            return io_fail(NPORE_IO_ERR_FORMAT, "not a BGZF file (bad member header)");
+        const size_t xlen = rd16(hd + 10);
+        const size_t at = cbuf.size();
+        cbuf.resize(at + xlen);
+        if (xlen && std::fread(&cbuf[at], 1, xlen, b->fh) != xlen) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF header");
+        size_t bsize = 0;
+        for (size_t q = at; q + 4 <= at + xlen;) {
+            const size_t sl = rd16(&cbuf[q + 2]);
+            if (cbuf[q] == 'B' && cbuf[q + 1] == 'C' && sl == 2 && q + 6 <= at + xlen) bsize = (size_t)rd16(&cbuf[q + 4]) + 1;
+            q += 4 + sl;
+        }
+        if (bsize < xlen + 20) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF member");
+        const size_t rest = bsize - 12 - xlen;                 // deflate data + CRC32 + ISIZE
+        cbuf.resize(at + rest);                                // the extra field is not needed any more: overwrite it
+        if (std::fread(&cbuf[at], 1, rest, b->fh) != rest) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF member");
+        Blk k;
+        k.coff = at; k.clen = rest - 8; k.crc = rd32(&cbuf[at + rest - 8]); k.ulen = rd32(&cbuf[at + rest - 4]); k.uoff = base + added;
+        added += k.ulen;
+        blks.push_back(k);
+    }
+    b->data.resize(base + added);
+    std::atomic<int> bad{0};
+    parallel_for((int64_t)blks.size(), b->n_threads, [&](int64_t lo, int64_t hi) {
+        z_stream zs;
+        for (int64_t k = lo; k < hi; k++) {
+            const Blk &m = blks[(size_t)k];
+            if (!m.ulen) continue;
+            std::memset(&zs, 0, sizeof(zs));
+            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+            zs.next_in = const_cast<Bytef *>(&cbuf[m.coff]); zs.avail_in = (uInt)m.clen;
+            zs.next_out = &b->data[m.uoff]; zs.avail_out = (uInt)m.ulen;
+            const int rc = inflate(&zs, Z_FINISH);
+            inflateEnd(&zs);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), &b->data[m.uoff], (uInt)m.ulen) != m.crc) { bad = 1; return; }
+        }
+    });
+    if (bad) return io_fail(NPORE_IO_ERR_FORMAT, "BGZF member failed to inflate (corrupt data or CRC mismatch)");
+    return NPORE_IO_OK;
+}
+
 int npore_bam_open(const char *path, int n_threads, npore_bam **out)
 {
     if (!path || !out) return io_fail(NPORE_IO_ERR_ARG, "null argument");
     *out = nullptr;
     FILE *fh = std::fopen(path, "rb");
     if (!fh) return io_fail(NPORE_IO_ERR_OPEN, std::string("cannot open ") + path);
-    std::fseek(fh, 0, SEEK_END);
-    const long fsz = std::ftell(fh);
-    std::fseek(fh, 0, SEEK_SET);
-    std::vector<uint8_t> file((size_t)std::max<long>(fsz, 0));
-    const size_t got = file.empty() ? 0 : std::fread(file.data(), 1, file.size(), fh);
-    std::fclose(fh);
-    if (got != file.size()) return io_fail(NPORE_IO_ERR_OPEN, std::string("short read on ") + path);
-
-    // ---- BGZF members: 12 fixed bytes, XLEN extra (subfield 'B','C' holds BSIZE = member size - 1), deflate data, CRC32, ISIZE
-    struct Blk { size_t coff, clen, uoff, ulen; uint32_t crc; };
-    std::vector<Blk> blks;
-    size_t p = 0, utotal = 0;
-    while (p < file.size()) {
-        if (p + 18 > file.size() || file[p] != 0x1f || file[p + 1] != 0x8b || file[p + 2] != 8 || !(file[p + 3] & 4))
-            return io_fail(NPORE_IO_ERR_FORMAT, "not a BGZF file (bad member header)");
-        const size_t xlen = rd16(&file[p + 10]);
-        size_t q = p + 12, xe = q + xlen, bsize = 0;
-        if (xe > file.size()) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF header");
-        while (q + 4 <= xe) {
-            const size_t sl = rd16(&file[q + 2]);
-            if (file[q] == 'B' && file[q + 1] == 'C' && sl == 2) bsize = (size_t)rd16(&file[q + 4]) + 1;
-            q += 4 + sl;
-        }
-        if (!bsize || p + bsize > file.size() || bsize < xlen + 20) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF member");
-        Blk b;
-        b.coff = xe; b.clen = bsize - xlen - 20;
-        b.crc = rd32(&file[p + bsize - 8]); b.ulen = rd32(&file[p + bsize - 4]); b.uoff = utotal;
-        utotal += b.ulen;
-        blks.push_back(b);
-        p += bsize;
-    }
     npore_bam *bam = new npore_bam();
-    bam->data.resize(utotal);
-    std::atomic<int> bad{0};
-    parallel_for((int64_t)blks.size(), n_threads, [&](int64_t lo, int64_t hi) {
-        z_stream zs;
-        for (int64_t k = lo; k < hi; k++) {
-            const Blk &b = blks[(size_t)k];
-            if (!b.ulen) continue;
-            std::memset(&zs, 0, sizeof(zs));
-            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-            zs.next_in = const_cast<Bytef *>(&file[b.coff]); zs.avail_in = (uInt)b.clen;
-            zs.next_out = &bam->data[b.uoff]; zs.avail_out = (uInt)b.ulen;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), &bam->data[b.uoff], (uInt)b.ulen) != b.crc) { bad = 1; return; }
+    bam->fh = fh; bam->n_threads = n_threads;
+    // ---- BAM header: magic, l_text, text, n_ref, (l_name, name, l_ref)*; members are loaded until it is complete
+    auto have = [&](size_t n) -> int {        // 1: n bytes available, 0: file ended first, <0: error
+        while (bam->data.size() < n) {
+            if (bam->eof) return 0;
+            const int rc = load_blocks(bam, std::max<size_t>(n - bam->data.size(), 1));
+            if (rc) return rc;
         }
-    });
-    if (bad) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "BGZF member failed to inflate (corrupt data or CRC mismatch)"); }
-    std::vector<uint8_t>().swap(file);
-
-    // ---- BAM header
-    const std::vector<uint8_t> &d = bam->data;
-    auto need = [&](size_t at, size_t n) { return at + n <= d.size(); };
-    if (!need(0, 12) || std::memcmp(d.data(), "BAM\1", 4) != 0) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "not a BAM file"); }
+        return 1;
+    };
+    auto bail = [&](int code, const char *what) { delete bam; return io_fail(code, what); };
+    int rc = have(12);
+    if (rc < 0) { delete bam; return rc; }
+    if (!rc || std::memcmp(bam->data.data(), "BAM\1", 4) != 0) return bail(NPORE_IO_ERR_FORMAT, "not a BAM file");
     size_t at = 4;
-    const size_t l_text = rd32(&d[at]); at += 4;
-    if (!need(at, l_text + 4)) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM header"); }
-    bam->text.assign((const char *)&d[at], l_text);
+    const size_t l_text = rd32(&bam->data[at]); at += 4;
+    if ((rc = have(at + l_text + 4)) <= 0) { if (rc < 0) { delete bam; return rc; } return bail(NPORE_IO_ERR_FORMAT, "truncated BAM header"); }
+    bam->text.assign((const char *)&bam->data[at], l_text);
     bam->text = bam->text.c_str();                    // drop NUL padding
     at += l_text;
-    const size_t n_ref = rd32(&d[at]); at += 4;
+    const size_t n_ref = rd32(&bam->data[at]); at += 4;
     for (size_t i = 0; i < n_ref; i++) {
-        if (!need(at, 4)) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM reference list"); }
-        const size_t l_name = rd32(&d[at]); at += 4;
-        if (!need(at, l_name + 4) || !l_name) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM reference list"); }
-        bam->ref_names.emplace_back((const char *)&d[at], l_name - 1); at += l_name;
-        bam->ref_lens.push_back((int64_t)rd32(&d[at])); at += 4;
+        if ((rc = have(at + 4)) <= 0) { if (rc < 0) { delete bam; return rc; } return bail(NPORE_IO_ERR_FORMAT, "truncated BAM reference list"); }
+        const size_t l_name = rd32(&bam->data[at]); at += 4;
+        if (!l_name || (rc = have(at + l_name + 4)) <= 0) { if (rc < 0) { delete bam; return rc; } return bail(NPORE_IO_ERR_FORMAT, "truncated BAM reference list"); }
+        bam->ref_names.emplace_back((const char *)&bam->data[at], l_name - 1); at += l_name;
+        bam->ref_lens.push_back((int64_t)rd32(&bam->data[at])); at += 4;
     }
-    // ---- record index, then the per-record columns in parallel
+    bam->head = at;
+    *out = bam;
+    return NPORE_IO_OK;
+}
+
+// Next window of records: drops the previous window, inflates members until at least max_bytes of record data are
+// available (<= 0: the rest of the file) and indexes the complete records.  Returns their number; 0 at end of file.
+int64_t npore_bam_advance(npore_bam *bam, int64_t max_bytes)
+{
+    if (!bam) return io_fail(NPORE_IO_ERR_ARG, "null handle");
+    bam->recs.clear();
+    if (bam->head) { bam->data.erase(bam->data.begin(), bam->data.begin() + (std::ptrdiff_t)bam->head); bam->head = 0; }
+    const size_t want = max_bytes > 0 ? (size_t)max_bytes : (size_t)-1;
     std::vector<int64_t> offs;
-    while (at + 4 <= d.size()) {
-        const size_t bs = rd32(&d[at]);
-        if (bs < 32 || !need(at + 4, bs)) { delete bam; return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM record"); }
-        offs.push_back((int64_t)at + 4);
-        at += 4 + bs;
+    size_t at = 0;
+    for (;;) {
+        // index the complete records present
+        while (at + 4 <= bam->data.size() && !(at >= want && !offs.empty())) {
+            const size_t bs = rd32(&bam->data[at]);
+            if (bs < 32) return io_fail(NPORE_IO_ERR_FORMAT, "corrupt BAM record (block_size < 32)");
+            if (at + 4 + bs > bam->data.size()) break;
+            offs.push_back((int64_t)at + 4);
+            at += 4 + bs;
+        }
+        if ((at >= want && !offs.empty()) || (bam->eof && (at + 4 > bam->data.size() || at + 4 + rd32(&bam->data[at]) > bam->data.size()))) break;
+        const size_t need = std::max<size_t>(want > at ? std::min<size_t>(want - at, (size_t)1 << 30) : 1, 1);
+        const int rc = load_blocks(bam, need);
+        if (rc) return rc;
     }
+    if (bam->eof && offs.empty() && at != bam->data.size())
+        return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM record at end of file");
+    bam->head = at;
+    const std::vector<uint8_t> &d = bam->data;
+    const int n_threads = bam->n_threads;
     bam->recs.resize(offs.size());
     parallel_for((int64_t)offs.size(), n_threads, [&](int64_t lo, int64_t hi) {
         for (int64_t k = lo; k < hi; k++) {
@@ -201,8 +246,7 @@ int npore_bam_open(const char *path, int n_threads, npore_bam **out)
             o.hp = find_hp(aux, end);
         }
     });
-    *out = bam;
-    return NPORE_IO_OK;
+    return (int64_t)bam->recs.size();
 }
 
 void npore_bam_close(npore_bam *b) { delete b; }

@@ -371,3 +371,36 @@ class Realigner:
         else:
             outs = [res.ops_str(i) for i in range(packed.n)]
         return outs, [res.scores(i).copy() for i in range(packed.n)], res.status[:packed.n].copy()
+
+
+class PipelinedRealigner:
+    """Several batches in flight on one GPU: `n_inflight` independent contexts, each with its own CUDA stream and host
+    thread.  While one batch is in its kernels, the next one's host->device copies and the previous one's device->host
+    copies proceed, and the tail of one forward kernel (SMs going idle) is filled by the head of the next.  Batches are
+    independent (bam.pyx:51), so nothing is shared between the contexts; results come back as futures, in submit order
+    if the caller keeps the futures in order."""
+
+    def __init__(self, sub_scores, np_scores, n_inflight=2, **kw):
+        import queue
+        from concurrent.futures import ThreadPoolExecutor
+        self.engines = [Realigner(sub_scores, np_scores, **kw) for _ in range(max(1, n_inflight))]
+        self._free = queue.SimpleQueue()
+        for e in self.engines:
+            self._free.put(e)
+        self._pool = ThreadPoolExecutor(len(self.engines))
+
+    def submit(self, packed: PackedBatch, flags: int = 0, result: BatchResult = None, pinned_result=False):
+        """Future of (BatchResult, stats dict) for npore_align_batch on the next free context."""
+        def work():
+            eng = self._free.get()
+            try:
+                res = eng.align_packed(packed, flags, result or eng.new_result(packed, flags, pinned=pinned_result))
+                return res, eng.stats()
+            finally:
+                self._free.put(eng)
+        return self._pool.submit(work)
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+        for e in self.engines:
+            e.close()

@@ -92,6 +92,17 @@ def test_native_reader_matches_python_reader(golden, tmp_path):
         blob = bamio.format_sam(nb, sel, g, words, off, n_threads=2).tobytes().decode()
         assert blob == "".join(sam_record(w, c) + "\n" for w, c in zip(want, kept))
         assert len(list(bamio.select_reads(nb, max_reads=1))[0][1]) == 1
+        # streaming: small windows (records straddle BGZF members and window ends) deliver the same records in order
+        st = bamio.NativeBam(path, n_threads=2, window_bytes=120)
+        seen, windows = [], 0
+        while st.advance():
+            windows += 1
+            gg = st.gather(np.arange(st.n))
+            seen += [(int(st.pos[k]), int(st.flag[k]), gg["seq_ascii"][gg["seq_off"][k]:gg["seq_off"][k + 1]].tobytes()) for k in range(st.n)]
+        allg = nb.gather(np.arange(nb.n))
+        assert seen == [(int(nb.pos[k]), int(nb.flag[k]), allg["seq_ascii"][allg["seq_off"][k]:allg["seq_off"][k + 1]].tobytes()) for k in range(nb.n)]
+        assert windows > 1 or nb.n < 3
+        st.close()
         nb.close()
     with pytest.raises(FileNotFoundError):
         bamio.NativeBam(str(tmp_path / "missing.bam"))
@@ -138,3 +149,9 @@ def test_realign_bam_end_to_end(golden, tables, tmp_path):
     n2 = bamio.realign_bam(bam, fasta, out_prefix=str(tmp_path / "out3"), argv=["x"], max_batch_ops=1500, regions=[("ref", 0, reads[3][6])])
     body3 = [l for l in open(str(tmp_path / "out3.sam")).read().splitlines() if not l.startswith("@")]
     assert n2 == len(body3) and body3 == [want[r[0]] for r in reads if r[3] < reads[3][6]]
+    # streamed in small windows, three batches in flight, capped read count
+    n3 = bamio.realign_bam(bam, fasta, out_prefix=str(tmp_path / "out4"), argv=["x"], max_batch_ops=1200, window_bytes=3000, n_inflight=3)
+    body4 = [l for l in open(str(tmp_path / "out4.sam")).read().splitlines() if not l.startswith("@")]
+    assert n3 == len(reads) and body4 == [want[r[0]] for r in reads]
+    n4 = bamio.realign_bam(bam, fasta, out_prefix=str(tmp_path / "out5"), argv=["x"], window_bytes=3000, max_reads=4)
+    assert n4 == 4 and [l for l in open(str(tmp_path / "out5.sam")).read().splitlines() if not l.startswith("@")] == [want[r[0]] for r in reads[:4]]

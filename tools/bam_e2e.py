@@ -1,5 +1,6 @@
 """BAM file in, realigned SAM file out: reads/s of npore_b200.bamio.realign_bam on the C2 workload (3,000 x 10 kb reads)
-with the time per phase (native BGZF/BAM decode, flat gather, GPU call incl. packing, native SAM formatting, file write),
+with the host time per phase (native BGZF/BAM decode, flat gather + submit, waiting for the GPU, native SAM formatting,
+file write; the GPU runs concurrently with the host phases of the neighbouring batches),
 next to the tuple API (get_read_data -> realign_reads), which is what a caller keeping the reference's per-read objects pays.
 usage: python tools/bam_e2e.py [n_reads]"""
 import os
