@@ -72,6 +72,21 @@ __device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n
         for (int h = tid; h < len; h += ANN_THREADS) {
             const int w = h >> 5, b = h & 31;
             const uint32_t cur = s_e[w];
+            {   // a chain head needs 2n equalities from h on (3 copies).  Positions of this word where such a stretch starts,
+                // from the 64-bit window cur | next (warp-uniform: most words have none and the warp moves on)
+                const uint64_t x = ((uint64_t)s_e[w + 1] << 32) | cur;
+                uint64_t y = x & (x >> 1);                                   // 2 ones
+                if (n >= 2) {
+                    const uint64_t y2 = y & (y >> 2);                        // 4 ones
+                    if (n == 2) y = y2;
+                    else if (n == 3) y = y2 & (y >> 4);                      // 6
+                    else {
+                        const uint64_t y4 = y2 & (y2 >> 4);                  // 8
+                        y = n == 4 ? y4 : n == 5 ? (y4 & (y >> 8)) : (y4 & (y2 >> 8));      // 10 / 12
+                    }
+                }
+                if (!(((uint32_t)y >> b) & 1u)) continue;
+            }
             // equalities immediately before h (only the first n matter)
             const uint64_t below = (((uint64_t)cur << 32) | (uint64_t)(w ? s_e[w - 1] : 0u)) << (32 - b);     // bit 63 = e[h-1]
             const int t = __clzll(~below | 1ull);
