@@ -181,15 +181,22 @@ __global__ void __launch_bounds__(FIN_WIDE) rle_word_kernel(const FinishArgs a)
     }
 }
 
-// ---- stack-like output list of run-length groups (merges equal neighbours, drops empty groups)
+// ---- stack-like output list of run-length groups (merges equal neighbours, drops empty groups).  The top group lives in
+// a register, so a sweep's loop-carried dependency never goes through memory (a store followed by a load of the same
+// word costs an L1/L2 round trip per group; the sweeps are latency-bound).
 struct GroupStack {
-    uint32_t *g; int m;
+    uint32_t *g; int m; uint32_t top;              // groups 0..m-2 are in g[], group m-1 is `top`
     __device__ __forceinline__ void push(uint32_t op, uint32_t len)
     {
         if (!len) return;
-        if (m > 0 && (g[m - 1] & 15u) == op) g[m - 1] += len << 4;
-        else g[m++] = (len << 4) | op;
+        if (m > 0 && (top & 15u) == op) top += len << 4;
+        else { if (m > 0) g[m - 1] = top; top = (len << 4) | op; m++; }
     }
+    __device__ __forceinline__ bool top_is(uint32_t op) const { return m > 0 && (top & 15u) == op; }
+    __device__ __forceinline__ uint32_t top_len() const { return top >> 4; }
+    __device__ __forceinline__ void pop() { m--; if (m > 0) top = g[m - 1]; }
+    __device__ __forceinline__ void shrink(uint32_t k) { top -= k << 4; if ((top >> 4) == 0u) pop(); }
+    __device__ __forceinline__ int finish() { if (m > 0) g[m - 1] = top; return m; }
 };
 
 // cig.pyx:102-159 on groups.  sp counts M ops and push_op runs passed (= position in `seq`, which is the reference for
@@ -197,54 +204,53 @@ struct GroupStack {
 // those M's, k = number of consecutive t with seq[sp-t-1] == seq[sp-t-1+L].
 __device__ __forceinline__ int rle_push_indels_left(const uint32_t *in, int m, uint32_t *out, const uint8_t *__restrict__ seq, uint32_t push_op)
 {
-    GroupStack st{out, 0};
+    GroupStack st{out, 0, 0u};
     int sp = 0;
     for (int g = 0; g < m; g++) {
         const uint32_t op = in[g] & 15u, len = in[g] >> 4;
         if (op != push_op) { st.push(op, len); if (op == 0u) sp += (int)len; continue; }
         int k = 0;
-        if (st.m > 0 && (st.g[st.m - 1] & 15u) == 0u) {
-            const int lim = min((int)(st.g[st.m - 1] >> 4), sp);
+        if (st.top_is(0u)) {
+            const int lim = min((int)st.top_len(), sp);
             while (k < lim && seq[sp - k - 1] == seq[sp - k - 1 + (int)len]) k++;
-            if (k) { st.g[st.m - 1] -= (uint32_t)k << 4; if ((st.g[st.m - 1] >> 4) == 0u) st.m--; }
+            if (k) st.shrink((uint32_t)k);
         }
         st.push(push_op, len);
         st.push(0u, (uint32_t)k);
         sp += (int)len;
     }
-    return st.m;
+    return st.finish();
 }
 
 // cig.pyx:164-192 on groups: an I run that follows a D run is moved in front of it
 __device__ __forceinline__ int rle_push_inss_thru_dels(const uint32_t *in, int m, uint32_t *out)
 {
-    GroupStack st{out, 0};
+    GroupStack st{out, 0, 0u};
     for (int g = 0; g < m; g++) {
         const uint32_t op = in[g] & 15u, len = in[g] >> 4;
-        if (op == 1u && st.m > 0 && (st.g[st.m - 1] & 15u) == 2u) {
-            const uint32_t d = st.g[st.m - 1] >> 4;
-            st.m--;
+        if (op == 1u && st.top_is(2u)) {
+            const uint32_t d = st.top_len();
+            st.pop();
             st.push(1u, len);
             st.push(2u, d);
         } else st.push(op, len);
     }
-    return st.m;
+    return st.finish();
 }
 
 // bam.pyx:78  .replace('ID','M') on groups: the last I of a run and the first D of the run that follows become one M
 __device__ __forceinline__ int rle_id_to_m(const uint32_t *in, int m, uint32_t *out)
 {
-    GroupStack st{out, 0};
+    GroupStack st{out, 0, 0u};
     for (int g = 0; g < m; g++) {
         const uint32_t op = in[g] & 15u, len = in[g] >> 4;
-        if (op == 2u && st.m > 0 && (st.g[st.m - 1] & 15u) == 1u) {
-            st.g[st.m - 1] -= 1u << 4;
-            if ((st.g[st.m - 1] >> 4) == 0u) st.m--;
+        if (op == 2u && st.top_is(1u)) {
+            st.shrink(1u);
             st.push(0u, 1u);
             st.push(2u, len - 1u);
         } else st.push(op, len);
     }
-    return st.m;
+    return st.finish();
 }
 
 // one item per WARP, lane 0 does the sweeps: 32 different sequential sweeps inside one warp would serialise
