@@ -525,10 +525,10 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
                     }
                 }
                 uint16_t *rowp = tbp + (size_t)d * (32 * TBS);
-                if (CPL == 2) *reinterpret_cast<uint32_t *>(rowp) = recs[0] | (recs[CPL - 1] << 16);
+                if (CPL == 2) __stcs(reinterpret_cast<unsigned int *>(rowp), recs[0] | (recs[CPL - 1] << 16));    // streamed once, read once by the traceback
                 else {
 #pragma unroll
-                    for (int k = 0; k < CPL; k++) rowp[k] = (uint16_t)recs[k];
+                    for (int k = 0; k < CPL; k++) __stcs(reinterpret_cast<unsigned short *>(rowp) + k, (unsigned short)recs[k]);
                 }
             }
             __syncwarp();
