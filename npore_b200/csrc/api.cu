@@ -124,11 +124,23 @@ template <int CPL>
 int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 {
     constexpr int WARPS = fwd_warps(CPL);
-    const size_t smem = (size_t)(WARPS + FWD_ALIGNED) * 4 * NP_RING * 32 * CPL * sizeof(float);
+    // rings are aligned to their size inside the CTA's shared window; the window starts 1 KB in (reserved) + the static
+    // arrays, so (ring - 1 KB) of slack always suffices -- a full extra ring would push 4 CTAs over the 164 KB carve-out
+    constexpr size_t RING = (size_t)4 * NP_RING * 32 * CPL * sizeof(float);
+    const size_t smem = (size_t)WARPS * RING + (FWD_ALIGNED ? RING - 1024 : 0);
     CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
+    {   // ask for the smallest shared-memory carve-out that holds the resident CTAs: the rest of the 256 KB is L1 for the
+        // score-table lookups (the default picked 196 KB where 164 KB is enough, leaving 56 instead of 92 KB of L1)
+        cudaFuncAttributes fattr;
+        CU(cudaFuncGetAttributes(&fattr, forward_kernel<CPL>));
+        const size_t need = (size_t)per_sm * (smem + fattr.sharedSizeBytes + 1024);
+        int pct = (int)((need * 100 + 233472 - 1) / 233472);
+        if (pct > 100) pct = 100;
+        CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    }
     ctx->stats.overflow_runs = per_sm * WARPS;      // resident forward warps per SM (diagnostic)
     int grid = std::min((n_sub + WARPS - 1) / WARPS, ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;

@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
     __syncthreads();
 #if FWD_ALIGNED
     const uint32_t smem_base = ((uint32_t)__cvta_generic_to_shared(smem) + RING_BYTES - 1u) & ~(RING_BYTES - 1u);
+    if (smem_base - (uint32_t)__cvta_generic_to_shared(smem) > RING_BYTES - 1024u) __trap();      // slack assumed by launch_forward
 #else
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 #endif
