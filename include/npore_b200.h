@@ -110,7 +110,7 @@ typedef struct npore_stats {
     float   ms_h2d, ms_d2h;
     int32_t launches;            /* kernel launches of the last npore_run                                    */
     int32_t n_sub_batches;
-    int32_t overflow_runs;       /* diagnostic: resident forward-kernel warps per SM of the last run          */
+    int32_t fwd_warps_per_sm;    /* resident forward-kernel warps per SM of the last run (occupancy achieved) */
     int32_t sm_count;
 } npore_stats;
 

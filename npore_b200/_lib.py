@@ -32,7 +32,7 @@ class Stats(C.Structure):
                 ("ms_plan", C.c_float), ("ms_annotate", C.c_float), ("ms_forward", C.c_float),
                 ("ms_traceback", C.c_float), ("ms_finish", C.c_float), ("ms_kernels_total", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float),
-                ("launches", C.c_int32), ("n_sub_batches", C.c_int32), ("overflow_runs", C.c_int32), ("sm_count", C.c_int32)]
+                ("launches", C.c_int32), ("n_sub_batches", C.c_int32), ("fwd_warps_per_sm", C.c_int32), ("sm_count", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

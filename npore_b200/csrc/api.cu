@@ -72,7 +72,7 @@ struct npore_ctx {
     DevBuf d_sub, d_np;
     // batch-resident
     DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
-        d_item_len, d_item_status, d_rleA, d_rleB, d_rle_len, d_rle_which, d_ops_off, d_rle_off, d_pack_ops, d_pack_rle, d_order, d_slots, d_counter, d_ovf, d_ovf_count;
+        d_item_len, d_item_status, d_rleA, d_rleB, d_rle_len, d_rle_which, d_ops_off, d_rle_off, d_pack_ops, d_pack_rle, d_order, d_slots, d_counter;
     // per sub-batch scratch
     DevBuf d_colrec, d_relaid, d_rowrec, d_raw_ref, d_raw_seq, d_tb, d_rr_q, d_rr_ctl, d_rr_state;
     int rr_slice = 512;
@@ -92,7 +92,6 @@ struct npore_ctx {
     cudaEvent_t ev[8]{};
     std::vector<cudaEvent_t> sub_ev;     // 4 per sub-batch
     std::string err;
-    static const int OVF_CAP = 1 << 16;
 };
 
 namespace {
@@ -141,7 +140,7 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
         if (pct > 100) pct = 100;
         CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
-    ctx->stats.overflow_runs = per_sm * WARPS;      // resident forward warps per SM (diagnostic)
+    ctx->stats.fwd_warps_per_sm = per_sm * WARPS;
     int grid = std::min((n_sub + WARPS - 1) / WARPS, ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
     forward_kernel<CPL><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);
@@ -212,8 +211,7 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     if (cudaMemcpy(ctx->d_sub.p, sub_scores, 25 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NPORE_ERR_CUDA);
     if (cudaMemcpy(ctx->d_np.p, np2.data(), np2.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(NPORE_ERR_CUDA);
-    if (ctx->d_counter.ensure(64) != cudaSuccess || ctx->d_ovf_count.ensure(64) != cudaSuccess ||
-        ctx->d_ovf.ensure(sizeof(OverflowRec) * npore_ctx::OVF_CAP) != cudaSuccess) return bail(NPORE_ERR_OOM);
+    if (ctx->d_counter.ensure(64) != cudaSuccess) return bail(NPORE_ERR_OOM);
     size_t fr = 0, tot = 0;
     cudaMemGetInfo(&fr, &tot);
     fwd_init_constants();
@@ -232,7 +230,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
                       &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
-                      &ctx->d_ovf, &ctx->d_ovf_count, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
+                      &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
     for (auto *b : bufs) b->release();
     for (auto &b : ctx->d_cm) b.release();
     ctx->d_chunk_dst.release(); ctx->d_part_cnt.release();
@@ -412,7 +410,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     CU(ctx->d_rr_ctl.ensure(64));
     CU(ctx->d_rr_state.ensure(sizeof(uint32_t) * fwd_rr_state_words(ctx->cpl) * (size_t)max_sub));
     if (nchunks) CU(cudaMemcpyAsync(ctx->d_slots.p, ctx->slots.data(), sizeof(ChunkSlot) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_ovf_count.p, 0, 4, ctx->stream));
 
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     // ---- plan
@@ -449,7 +446,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         fa.ref_codes = aa.ref_codes; fa.seq_codes = aa.seq_codes; fa.colrec = aa.colrec; fa.relaid = aa.relaid; fa.rowrec = aa.rowrec;
         fa.tb = ctx->d_tb.as<uint16_t>(); fa.np_tab = ctx->d_np.as<float>(); fa.sub_tab = ctx->d_sub.as<float>();
         fa.out = ctx->d_chunk_out.as<ChunkOut>();
-        fa.ovf = ctx->d_ovf.as<OverflowRec>(); fa.ovf_count = ctx->d_ovf_count.as<int>(); fa.ovf_cap = npore_ctx::OVF_CAP;
         fa.P = ctx->P;
         fa.rr_q = ctx->d_rr_q.as<int>(); fa.rr_mask = rr_cap - 1; fa.rr_ctl = ctx->d_rr_ctl.as<int>();
         fa.rr_state = ctx->d_rr_state.as<uint32_t>(); fa.rr_slice = ctx->rr_slice;
@@ -474,7 +470,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         ta.chunks = aa.chunks; ta.slots = aa.slots; ta.order = aa.order; ta.n = sb.count; ta.items = aa.items;
         ta.bits = fa.bits; ta.cum = ctx->d_cum.as<uint32_t>(); ta.ref_codes = aa.ref_codes; ta.seq_codes = aa.seq_codes;
         ta.tb = fa.tb; ta.ops = ctx->d_scratch_ops.as<uint8_t>(); ta.out = fa.out;
-        ta.ovf = fa.ovf; ta.ovf_count = fa.ovf_count; ta.ovf_cap = fa.ovf_cap;
         ta.r = ctx->P.r; ta.W = ctx->P.W; ta.cpl = ctx->cpl; ta.tbs = ctx->tbs;
         traceback_kernel<<<(sb.count + TB_THREADS / 32 - 1) / (TB_THREADS / 32), TB_THREADS, 0, ctx->stream>>>(ta);
         CU(cudaGetLastError()); S.launches++;
@@ -556,9 +551,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
 #ifdef FWD_SPIN_DEBUG
     { int sp = 0; cudaMemcpy(&sp, ctx->d_rr_ctl.as<int>() + 8, 4, cudaMemcpyDeviceToHost); S.n_sub_batches = sp; }
 #endif
-    int ovf = 0;
-    CU(cudaMemcpy(&ovf, ctx->d_ovf_count.p, 4, cudaMemcpyDeviceToHost));
-    if (ovf > npore_ctx::OVF_CAP) return fail(ctx, NPORE_ERR_CAPACITY, "run-overflow list exhausted");
     ctx->ran = true;
     return NPORE_OK;
 }

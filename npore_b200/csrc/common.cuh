@@ -62,8 +62,6 @@ struct ChunkOut {
     int32_t len;        // emitted ops
 };
 
-struct OverflowRec { int32_t chunk, d, bc, run; };
-
 struct AlignParams {
     int r, W, max_n, max_l, max_b_rows;
     int np_dim, np_clamp;       // table side (101) and the index clamp max_l-1 (aln.pyx:269-272 as called at :615)

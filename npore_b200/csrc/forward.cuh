@@ -63,7 +63,6 @@ struct ForwardArgs {
     const float *np_tab;          // [np_n][np_dim][np_dim]
     const float *sub_tab;         // [5][5]  indexed [seq_base][ref_base]
     ChunkOut *out;                // indexed by chunk id
-    OverflowRec *ovf; int *ovf_count; int ovf_cap;
     // round-robin time slicing (FWD_RR): run queue + per-chunk saved state
     int *rr_q; int rr_mask; int *rr_ctl;      // ctl[0] head, ctl[1] tail, ctl[2] finished chunks
     uint32_t *rr_state; int rr_slice;

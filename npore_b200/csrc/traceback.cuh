@@ -21,7 +21,6 @@ struct TracebackArgs {
     const uint16_t *tb;
     uint8_t *ops;                 // op scratch, item regions at ItemDesc::out_off
     ChunkOut *out;
-    const OverflowRec *ovf; const int *ovf_count; int ovf_cap;
     int r, W, cpl, tbs;
 };
 

@@ -36,7 +36,7 @@ def run(eng, cases, flags, reps=3):
 
 def row(name, st, tk, te):
     return (f"| {name} | {st['n_items']} | {st['n_chunks']} | {st['n_cu'] / 1e9:.2f} | {tk * 1e3:.1f} | {st['n_cu'] / tk / 1e9:.1f} | "
-            f"{te * 1e3:.1f} | {st['n_cu'] / te / 1e9:.1f} | {st['tb_bytes'] / 2**30:.2f} | {st['n_sub_batches']} | {st['overflow_runs']} |")
+            f"{te * 1e3:.1f} | {st['n_cu'] / te / 1e9:.1f} | {st['tb_bytes'] / 2**30:.2f} | {st['n_sub_batches']} | {st['fwd_warps_per_sm']} |")
 
 
 def main():
