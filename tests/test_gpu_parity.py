@@ -239,6 +239,41 @@ def test_full_c2_properties(tables):
     eng.close()
 
 
+def test_c3_shard_scale_properties(tables, monkeypatch):
+    """BASELINE.json configs[2] is 192,000 reads over 8 GPUs; this is half of one GPU's share (12,000 x 10 kb, 14.6 G cell
+    updates, ~30 GB of traceback rows) under a scratch budget that forces several sub-batches: every CIGAR consumes
+    exactly its read and reference span, the result does not depend on how the reads are batched, and a sample is
+    bit-exact (op strings and chunk scores) against the oracle."""
+    import bench
+    from npore_b200.engine import PackedBatch, Realigner
+    S, NP = tables
+    _, reads = bench.make_workload(20260103, 4_000_000, 12_000, 10_000, NP)
+    packed = bench.pack_reads(reads, pinned=False)
+    monkeypatch.setenv("NPORE_SCRATCH_MB", "12000")
+    eng = Realigner(S, NP)
+    res = eng.align_packed(packed, 0, eng.new_result(packed, 0, pinned=False))
+    st = eng.stats()
+    assert st["n_sub_batches"] >= 3 and st["n_items"] == 12_000 and not res.status[:packed.n].any()
+    n = packed.n
+    off = res.ops_off[:n + 1]
+    ops = res.ops[:off[n]]
+    not_i = np.concatenate(([0], np.cumsum(ops != ord("I"))))
+    not_d = np.concatenate(([0], np.cumsum(ops != ord("D"))))
+    assert np.array_equal(not_i[off[1:]] - not_i[off[:-1]], packed.ref_len) and np.array_equal(not_d[off[1:]] - not_d[off[:-1]], packed.seq_len)
+    assert set(np.unique(ops).tolist()) <= {ord(c) for c in "=XID"}
+    # batching invariance: the second half alone gives the same op strings and scores
+    half = n // 2
+    sub = PackedBatch.from_strings([r[9] for r in reads[half:]], [r[7] for r in reads[half:]], [r[5] for r in reads[half:]])
+    res2 = eng.align_packed(sub, 0, eng.new_result(sub, 0, pinned=False))
+    assert np.array_equal(res2.ops[:res2.ops_off[sub.n]], ops[off[half]:])
+    assert np.array_equal(res2.chunk_scores[:res2.score_off[sub.n]], res.chunk_scores[res.score_off[half]:res.score_off[n]])
+    for k in range(5, n, 397):
+        rd = reads[k]
+        want, wsc, _ = oracle.align(oracle.bases_to_int(rd[9]), oracle.bases_to_int(rd[7]), cig.expand_cigar(rd[5]), S, NP, return_scores=True)
+        assert res.ops_str(k) == want and np.array_equal(res.scores(k), wsc)
+    eng.close()
+
+
 @pytest.mark.parametrize("r", [10, 30, 60, 100])
 def test_c4_long_reads_band_and_window_sweep(tables, engine_factory, r):
     """BASELINE.json configs[3]: 50-100 kb reads, band radius x max_b_rows sweep (many chunks per read)."""
