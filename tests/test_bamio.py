@@ -112,6 +112,66 @@ def test_native_reader_matches_python_reader(golden, tmp_path):
         bamio.NativeBam(str(bad))
 
 
+def test_native_reader_random_stress(tmp_path):
+    """Seeded random BAMs (empty reads, clips, all op kinds, missing qualities, long names, filtered flags) streamed in
+    random window sizes on random thread counts: every record equals the pure-Python decode."""
+    rng = np.random.default_rng(5)
+    for trial in range(25):
+        recs = []
+        for k in range(int(rng.integers(0, 40))):
+            L = int(rng.integers(0, 400))
+            seq = "".join(rng.choice(list("ACGTNacgtRY"), size=L)) if L else ""
+            ops, rem, tail = [], L, 0
+            if L and rng.random() < 0.3:
+                ops.append((int(rng.integers(1, 5)), "H"))
+            if rem > 4 and rng.random() < 0.4:
+                c = int(rng.integers(1, 4)); ops.append((c, "S")); rem -= c
+            if rem > 4 and rng.random() < 0.4:
+                tail = int(rng.integers(1, 4)); rem -= tail
+            while rem > 0:
+                m = int(rng.integers(1, rem + 1)); ops.append((m, "M=X"[int(rng.integers(0, 3))])); rem -= m
+                if rem > 0 and rng.random() < 0.5:
+                    ops.append((int(rng.integers(1, 4)), "D"))
+                if rem > 1 and rng.random() < 0.5:
+                    i = int(rng.integers(1, min(3, rem))); ops.append((i, "I")); rem -= i
+            if tail:
+                ops.append((tail, "S"))
+            merged = []
+            for ln, op in ops:
+                if merged and merged[-1][1] == op:
+                    merged[-1] = (merged[-1][0] + ln, op)
+                else:
+                    merged.append((ln, op))
+            recs.append({"name": f"r{k}_{'x' * int(rng.integers(0, 20))}", "flag": int(rng.choice([0, 16, 256, 4, 2048, 1024])),
+                         "ref_id": int(rng.integers(0, 2)), "pos": int(rng.integers(0, 900)), "mapq": int(rng.integers(0, 61)), "cigar": merged,
+                         "seq": seq, "qual": None if (rng.random() < 0.3 or L == 0) else bytes(rng.integers(0, 60, size=L).astype(np.uint8)),
+                         "tags": {"HP": int(rng.integers(0, 3))} if rng.random() < 0.5 else {}})
+        path = str(tmp_path / f"s{trial}.bam")
+        bamio.write_bam(path, "@HD\tVN:1.6\n", [("a", 5000), ("b", 4000)], recs)
+        py = list(bamio.read_bam(path)[2])
+        nb = bamio.NativeBam(path, n_threads=int(rng.integers(1, 5)), window_bytes=int(rng.integers(40, 3000)))
+        k = 0
+        while nb.advance():
+            g = nb.gather(np.arange(nb.n))
+            for i in range(nb.n):
+                r = py[k]; k += 1
+                ops, lens = r["cigar"] & 15, r["cigar"] >> 4
+                lead = int(lens[0]) if len(ops) and ops[0] == 4 else (int(lens[1]) if len(ops) > 1 and ops[0] == 5 and ops[1] == 4 else 0)
+                trail = int(lens[-1]) if len(ops) and ops[-1] == 4 else (int(lens[-2]) if len(ops) > 1 and ops[-1] == 5 and ops[-2] == 4 else 0)
+                cut = lambda a, o: a[g[o][i]:g[o][i + 1]]   # noqa: E731
+                assert cut(g["seq_ascii"], "seq_off").tobytes().decode() == r["seq"][lead:len(r["seq"]) - trail].upper()
+                assert cut(g["names"], "name_off").tobytes().decode() == r["name"]
+                assert (nb.pos[i], nb.flag[i], nb.mapq[i], nb.hp[i]) == (r["pos"], r["flag"], r["mapq"], int(r["tags"].get("HP", 0)))
+                assert nb.end[i] == r["pos"] + int(lens[np.isin(ops, (0, 2, 3, 7, 8))].sum())
+                assert np.array_equal(cut(g["cigar"], "cig_off"), r["cigar"][(ops != 4) & (ops != 5)])
+                if r["qual"] is not None and len(r["seq"]):
+                    assert nb.has_qual[i] == 1 and cut(g["qual_ascii"], "seq_off").tobytes() == (r["qual"][lead:len(r["qual"]) - trail] + np.uint8(33)).tobytes()
+                elif len(r["seq"]):
+                    assert nb.has_qual[i] == 0
+        assert k == len(py) and nb.advance() == 0
+        nb.close()
+
+
 def test_header(tmp_path):
     out = tmp_path / "d" / "o.sam"
     bamio.create_header(str(out), [("chr1", 100), ("chr2", 50)], argv=["realign.py", "--bam", "x"])
