@@ -513,8 +513,16 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
             CU(cudaGetLastError()); S.launches += 2;
         } else CU(cudaMemsetAsync(ctx->d_rle_len.p, 0, sizeof(int32_t) * (size_t)n, ctx->stream));
         if (flags & NPORE_OUT_STANDARDIZE) {
-            standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa);
+            // items with many run-length groups (haplotypes) get a whole CTA each; NPORE_STD_LONG_MIN overrides the split (tests)
+            int long_min = 4096;
+            if (const char *e = getenv("NPORE_STD_LONG_MIN")) long_min = std::max(1, atoi(e));
+            const bool any_long = max_ops >= long_min;              // an item cannot have more groups than ops
+            standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa, any_long ? long_min : 0x7fffffff);
             CU(cudaGetLastError()); S.launches++;
+            if (any_long) {
+                standardize_long_kernel<<<n, FIN_WIDE, 0, ctx->stream>>>(fa, long_min);
+                CU(cudaGetLastError()); S.launches++;
+            }
             if (want_ops) {
                 if (parts > 1) { expand_count_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa); S.launches++; }
                 expand_fill_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa);

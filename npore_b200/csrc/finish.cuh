@@ -202,7 +202,8 @@ struct GroupStack {
 // cig.pyx:102-159 on groups.  sp counts M ops and push_op runs passed (= position in `seq`, which is the reference for
 // push_op == D and the read for push_op == I).  A run of push_op of length L preceded by an M group moves left over k of
 // those M's, k = number of consecutive t with seq[sp-t-1] == seq[sp-t-1+L].
-__device__ __forceinline__ int rle_push_indels_left(const uint32_t *in, int m, uint32_t *out, const uint8_t *__restrict__ seq, uint32_t push_op)
+__device__ __forceinline__ int rle_push_indels_left(const uint32_t *in, int m, uint32_t *out, const uint8_t *__restrict__ seq, uint32_t push_op,
+                                                    const int32_t *eq_run = nullptr)
 {
     GroupStack st{out, 0, 0u};
     int sp = 0;
@@ -212,7 +213,8 @@ __device__ __forceinline__ int rle_push_indels_left(const uint32_t *in, int m, u
         int k = 0;
         if (st.top_is(0u)) {
             const int lim = min((int)st.top_len(), sp);
-            while (k < lim && seq[sp - k - 1] == seq[sp - k - 1 + (int)len]) k++;
+            if (eq_run) k = min(eq_run[g], lim);
+            else while (k < lim && seq[sp - k - 1] == seq[sp - k - 1 + (int)len]) k++;
             if (k) st.shrink((uint32_t)k);
         }
         st.push(push_op, len);
@@ -220,6 +222,33 @@ __device__ __forceinline__ int rle_push_indels_left(const uint32_t *in, int m, u
         sp += (int)len;
     }
     return st.finish();
+}
+
+// The base comparisons of rle_push_indels_left do not depend on the stack: for the run of push_op at group g,
+// eq_run[g] = number of consecutive t with seq[sp-t-1] == seq[sp-t-1+len], sp = ops of kind M / push_op before g.
+// The whole warp computes them (a scan for sp, one lane per run), so the cold byte loads of all runs overlap instead of
+// sitting one after the other inside the sequential sweep.
+__device__ __forceinline__ void rle_eq_runs(const uint32_t *in, int m, const uint8_t *__restrict__ seq, uint32_t push_op, int32_t *eq_run)
+{
+    const int lane = threadIdx.x & 31;
+    int carry = 0;
+    for (int base = 0; base < m; base += 32) {
+        const int g = base + lane;
+        const uint32_t w = g < m ? in[g] : 0u, op = w & 15u;
+        const int len = (int)(w >> 4);
+        const int adv = (g < m && (op == 0u || op == push_op)) ? len : 0;
+        int x = adv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(NP_FULL, x, o); if (lane >= o) x += y; }
+        const int sp = carry + x - adv;
+        if (g < m && op == push_op) {
+            int k = 0;
+            while (k < sp && seq[sp - k - 1] == seq[sp - k - 1 + len]) k++;
+            eq_run[g] = k;
+        }
+        carry += __shfl_sync(NP_FULL, x, 31);
+    }
+    __syncwarp();
 }
 
 // cig.pyx:164-192 on groups: an I run that follows a D run is moved in front of it
@@ -253,23 +282,164 @@ __device__ __forceinline__ int rle_id_to_m(const uint32_t *in, int m, uint32_t *
     return st.finish();
 }
 
-// one item per WARP, lane 0 does the sweeps: 32 different sequential sweeps inside one warp would serialise
-__global__ void __launch_bounds__(FIN_THREADS) standardize_kernel(const FinishArgs a)
+// one item per WARP: lane 0 does the sweeps (32 different sequential sweeps inside one warp would serialise), all lanes
+// prepare the base comparisons of the two push_indels_left sweeps.  The comparison results go to the upper half of the
+// input buffer's item region (capacity Lref+Lseq words, of which the groups use the first m).
+__global__ void __launch_bounds__(FIN_THREADS) standardize_kernel(const FinishArgs a, int long_min_groups)
 {
     const int it = blockIdx.x * (FIN_THREADS / 32) + (threadIdx.x >> 5);
-    if (it >= a.n_items || (threadIdx.x & 31) != 0) return;
+    if (it >= a.n_items) return;
+    if (a.rle_len[it] >= long_min_groups) return;                 // standardize_long_kernel's
+    const bool lead = (threadIdx.x & 31) == 0;
     const ItemDesc &I = a.items[it];
     uint32_t *A = a.rleA + I.out_off, *B = a.rleB + I.out_off;
     const uint8_t *ref = a.ref_codes + I.ref_start, *seq = a.seq_codes + I.seq_start;
+    const int cap = I.total_ops;
+    int32_t *E = reinterpret_cast<int32_t *>(A + cap / 2);
     int m = a.rle_len[it];
-    m = rle_push_indels_left(A, m, B, ref, 2u);
-    m = rle_push_inss_thru_dels(B, m, A);
-    m = rle_push_indels_left(A, m, B, seq, 1u);
+    bool pre = 2 * m <= cap;
+    if (pre) rle_eq_runs(A, m, ref, 2u, E);
+    if (lead) {
+        m = rle_push_indels_left(A, m, B, ref, 2u, pre ? E : nullptr);
+        m = rle_push_inss_thru_dels(B, m, A);
+    }
+    m = __shfl_sync(NP_FULL, m, 0);
+    __threadfence_block();
+    __syncwarp();
+    pre = 2 * m <= cap;
+    if (pre) rle_eq_runs(A, m, seq, 1u, E);
+    if (!lead) return;
+    m = rle_push_indels_left(A, m, B, seq, 1u, pre ? E : nullptr);
     m = rle_push_inss_thru_dels(B, m, A);
     m = rle_id_to_m(A, m, B);
     int tot = 0;
     for (int g = 0; g < m; g++) tot += (int)(B[g] >> 4);
     a.rle_len[it] = m; a.rle_which[it] = 1; a.item_len[it] = tot;
+}
+
+// ---- the same five sweeps for LONG items (whole-contig haplotypes: 1e4..1e6 groups), one CTA per item.
+// A single lane needs ~150 ns per group and sweep; here the group list is cut into segments at M groups that no shift
+// can consume (for the push sweeps: the equality run of the next indel is shorter than the M group; for the other sweeps:
+// any M group), every thread runs the SAME sequential routine on its own segment, and the segment outputs are
+// concatenated and equal neighbours merged.  Anything that does not fit the scratch layout falls back to one thread.
+#define STDL_BLOCK 48
+
+__device__ __forceinline__ bool stdl_safe_cut(const uint32_t *X, int m, int g, int kind, uint32_t push_op, const int32_t *E)
+{
+    if (g == 0) return true;
+    if ((X[g] & 15u) != 0u) return false;
+    if (kind != 0) return true;                                   // thru_dels / id_to_m: every M group separates
+    return g + 1 >= m || (X[g + 1] & 15u) != push_op || E[g + 1] < (int)(X[g] >> 4);
+}
+
+// one sweep: dense X[0,m) -> dense Y[0,m'); kind 0 = push_indels_left(push_op, seq), 1 = push_inss_thru_dels, 2 = id_to_m
+__device__ int stdl_sweep(int kind, uint32_t push_op, const uint8_t *__restrict__ seq, uint32_t *X, int m, uint32_t *Y, int cap, int *s_w)
+{
+    __shared__ int s_m;
+    const int tid = threadIdx.x;
+    const int nblk = (m + STDL_BLOCK - 1) / STDL_BLOCK;
+    const bool fits = m > 0 && (long long)4 * m + 3ll * (nblk + 2) + 64 <= cap;
+    if (!fits) {                                                  // sequential fallback (also m == 0)
+        if (tid == 0)
+            s_m = kind == 0 ? rle_push_indels_left(X, m, Y, seq, push_op) : kind == 1 ? rle_push_inss_thru_dels(X, m, Y) : rle_id_to_m(X, m, Y);
+        __syncthreads();
+        const int r = s_m;
+        __syncthreads();
+        return r;
+    }
+    int32_t *E = reinterpret_cast<int32_t *>(X + cap / 2);         // [m]   equality runs (push sweeps)
+    int32_t *S = reinterpret_cast<int32_t *>(Y + cap) - (nblk + 2);   // [nblk+1] segment starts
+    int32_t *Cn = S - (nblk + 2), *O = Cn - (nblk + 2);           // [nblk+1] output counts, offsets
+    if (kind == 0) {                                              // CTA-wide rle_eq_runs
+        int carry = 0;
+        for (int base = 0; base < m; base += FIN_WIDE) {
+            const int g = base + tid;
+            const uint32_t w = g < m ? X[g] : 0u, op = w & 15u;
+            const int len = (int)(w >> 4);
+            const int adv = (g < m && (op == 0u || op == push_op)) ? len : 0;
+            int tot;
+            const int sp = carry + fin_block_scan<FIN_WIDE>(adv, s_w, tot) - adv;
+            if (g < m && op == push_op) {
+                int k = 0;
+                while (k < sp && seq[sp - k - 1] == seq[sp - k - 1 + len]) k++;
+                E[g] = k;
+            }
+            carry += tot;
+        }
+        __syncthreads();
+    }
+    for (int b = tid; b <= nblk; b += FIN_WIDE) {                 // segment b = [S[b], S[b+1])
+        int g = min(b * STDL_BLOCK, m);
+        while (g < m && !stdl_safe_cut(X, m, g, kind, push_op, E)) g++;
+        S[b] = g;
+    }
+    __syncthreads();
+    for (int b = tid; b < nblk; b += FIN_WIDE) {
+        const int g0 = S[b], n = S[b + 1] - g0;
+        int c = 0;
+        if (n > 0) {
+            uint32_t *out = Y + 2 * g0;
+            c = kind == 0 ? rle_push_indels_left(X + g0, n, out, seq, push_op, E + g0)
+              : kind == 1 ? rle_push_inss_thru_dels(X + g0, n, out) : rle_id_to_m(X + g0, n, out);
+        }
+        Cn[b] = c;
+    }
+    __syncthreads();
+    int carry = 0;
+    for (int base = 0; base < nblk; base += FIN_WIDE) {
+        const int b = base + tid;
+        const int c = b < nblk ? Cn[b] : 0;
+        int tot;
+        const int x = fin_block_scan<FIN_WIDE>(c, s_w, tot);
+        if (b < nblk) O[b] = carry + x - c;
+        carry += tot;
+    }
+    const int md = carry;                                         // groups before merging
+    __syncthreads();
+    for (int b = tid; b < nblk; b += FIN_WIDE) {                  // dense concatenation into X (its old contents are dead)
+        const uint32_t *src = Y + 2 * S[b];
+        uint32_t *dst = X + O[b];
+        for (int j = 0, c = Cn[b]; j < c; j++) dst[j] = src[j];
+    }
+    __syncthreads();
+    carry = 0;                                                    // merge equal neighbours: X[0,md) -> Y[0,m')
+    for (int base = 0; base < md; base += FIN_WIDE) {
+        const int j = base + tid;
+        const uint32_t w = j < md ? X[j] : 0u;
+        const int head = (j < md && (j == 0 || (X[j - 1] & 15u) != (w & 15u))) ? 1 : 0;
+        int tot;
+        const int x = fin_block_scan<FIN_WIDE>(head, s_w, tot);
+        if (head) {
+            uint32_t acc = w;
+            for (int t = j + 1; t < md && (X[t] & 15u) == (w & 15u); t++) acc += X[t] & ~15u;
+            Y[carry + x - 1] = acc;
+        }
+        carry += tot;
+    }
+    __syncthreads();
+    return carry;
+}
+
+__global__ void __launch_bounds__(FIN_WIDE) standardize_long_kernel(const FinishArgs a, int min_groups)
+{
+    __shared__ int s_w[FIN_WIDE / 32];
+    const int it = blockIdx.x;
+    int m = a.rle_len[it];
+    if (m < min_groups) return;                                   // (short items: standardize_kernel)
+    const ItemDesc &I = a.items[it];
+    uint32_t *A = a.rleA + I.out_off, *B = a.rleB + I.out_off;
+    const uint8_t *ref = a.ref_codes + I.ref_start, *seq = a.seq_codes + I.seq_start;
+    const int cap = I.total_ops;
+    m = stdl_sweep(0, 2u, ref, A, m, B, cap, s_w);
+    m = stdl_sweep(1, 0u, nullptr, B, m, A, cap, s_w);
+    m = stdl_sweep(0, 1u, seq, A, m, B, cap, s_w);
+    m = stdl_sweep(1, 0u, nullptr, B, m, A, cap, s_w);
+    m = stdl_sweep(2, 0u, nullptr, A, m, B, cap, s_w);
+    int part = 0;
+    for (int g = threadIdx.x; g < m; g += FIN_WIDE) part += (int)(B[g] >> 4);
+    int tot;
+    fin_block_scan<FIN_WIDE>(part, s_w, tot);
+    if (threadIdx.x == 0) { a.rle_len[it] = m; a.rle_which[it] = 1; a.item_len[it] = tot; }
 }
 
 // ---- run-length words -> chars (the expanded 'MID' string realign_hap returns), two part-parallel steps
