@@ -3,7 +3,7 @@
 //
 // Pipeline of one batch (all on one stream of one B200):
 //   upload   : items / base codes / RLE CIGARs -> HBM
-//   run      : plan_kernel      (aln.pyx:386-392  D/I bit string, rank arrays, chunk descriptors)
+//   run      : plan_* kernels   (aln.pyx:386-392  D/I bit string, rank arrays, chunk descriptors)
 //              per sub-batch of chunks, largest first (scratch bounded by the memory budget):
 //                annotate_kernel  (aln.pyx:179-251  np-info records of both slices of every chunk)
 //                forward_kernel   (aln.pyx:465-667  the recurrence; persistent warps, one chunk per warp)
@@ -413,11 +413,21 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
 
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     // ---- plan
+    int max_ops = 1;
+    for (const ItemDesc &I : ctx->items) max_ops = std::max(max_ops, I.total_ops);
+    const int parts = std::min(FIN_MAX_PARTS, (max_ops + 32767) / 32768);     // slices per item for the per-item kernels
     if (n) {
-        plan_kernel<<<n, PLAN_THREADS, 0, ctx->stream>>>(ctx->d_items.as<ItemDesc>(), n, ctx->d_rle.as<uint32_t>(), ctx->d_grp.as<int32_t>(),
-                                                         ctx->d_bits.as<uint32_t>(), ctx->d_cum.as<uint32_t>(), ctx->d_chunks.as<ChunkDesc>(),
-                                                         ctx->P.max_b_rows);
-        CU(cudaGetLastError()); S.launches++;
+        CU(ctx->d_part_cnt.ensure(sizeof(int32_t) * (size_t)n * parts));
+        PlanArgs pa{};
+        pa.items = ctx->d_items.as<ItemDesc>(); pa.n_items = n; pa.rle = ctx->d_rle.as<uint32_t>(); pa.grp_off = ctx->d_grp.as<int32_t>();
+        pa.bits = ctx->d_bits.as<uint32_t>(); pa.cum = ctx->d_cum.as<uint32_t>(); pa.chunks = ctx->d_chunks.as<ChunkDesc>();
+        pa.max_b_rows = ctx->P.max_b_rows; pa.parts = parts; pa.part_cnt = ctx->d_part_cnt.as<int32_t>();
+        const dim3 grid_np(n, parts);
+        plan_groups_kernel<<<n, PLAN_THREADS, 0, ctx->stream>>>(pa);
+        plan_bits_kernel<<<grid_np, PLAN_THREADS, 0, ctx->stream>>>(pa);
+        plan_cum_kernel<<<grid_np, PLAN_THREADS, 0, ctx->stream>>>(pa);
+        plan_chunks_kernel<<<grid_np, PLAN_THREADS, 0, ctx->stream>>>(pa);
+        CU(cudaGetLastError()); S.launches += 4;
     }
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     float ms_ann = 0, ms_fwd = 0, ms_tb = 0;
@@ -492,9 +502,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         fa.to_m = (flags & NPORE_OUT_STANDARDIZE) ? 1 : 0;
         fa.ops_off = ctx->d_ops_off.as<int64_t>(); fa.rle_off = ctx->d_rle_off.as<int64_t>();
         fa.pack_ops = ctx->d_pack_ops.as<uint8_t>(); fa.pack_rle = ctx->d_pack_rle.as<uint32_t>();
-        int max_ops = 1;
-        for (const ItemDesc &I : ctx->items) max_ops = std::max(max_ops, I.total_ops);
-        const int parts = std::min(FIN_MAX_PARTS, (max_ops + 32767) / 32768);
         CU(ctx->d_chunk_dst.ensure(sizeof(int32_t) * (size_t)std::max<int64_t>(ctx->n_chunks, 1)));
         CU(ctx->d_part_cnt.ensure(sizeof(int32_t) * (size_t)n * parts));
         fa.chunks = ctx->d_chunks.as<ChunkDesc>(); fa.n_chunks = (int)ctx->n_chunks;

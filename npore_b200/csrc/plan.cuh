@@ -4,7 +4,7 @@
 //     inss[g] (aln.pyx:279-292) is then a rank query: cumI[g>>5] + popc(low bits); dels[g] = g - inss[g]
 //     (aln.pyx:296-311), so the two int32[P+1] prefix arrays of the reference are never materialised.
 //   * get_breaks (aln.pyx:344-358) -> one ChunkDesc per chunk, including the "don't split a DI pair" shift.
-// One CTA per item; the three phases are block-wide scans over the item's RLE words / bit words.
+// Block-wide scans over the item's RLE words / bit words (kernels at the end of this file).
 #pragma once
 #include "common.cuh"
 
@@ -38,25 +38,36 @@ __device__ __forceinline__ uint32_t plan_rank(const uint32_t *bits, const uint32
     return cum[g >> 5] + __popc(w & ((1u << (g & 31)) - 1u));
 }
 
-__global__ void __launch_bounds__(PLAN_THREADS)
-plan_kernel(ItemDesc *items, int n_items, const uint32_t *__restrict__ rle, int32_t *__restrict__ grp_off,
-            uint32_t *__restrict__ bits, uint32_t *__restrict__ cum, ChunkDesc *__restrict__ chunks, int max_b_rows)
+// The prologue runs as four kernels so that an item of any length (a 64 Mb haplotype has 4e6 bit words) is not one
+// CTA's job: groups (1 CTA / item), bit words + popcount partial sums (items x parts), popcount prefix (items x parts),
+// chunk descriptors (items x parts).  `parts` comes from the largest item of the batch (1 for read batches).
+struct PlanArgs {
+    ItemDesc *items; int n_items;
+    const uint32_t *rle; int32_t *grp_off;
+    uint32_t *bits, *cum;
+    ChunkDesc *chunks;
+    int max_b_rows;
+    int parts; int32_t *part_cnt;        // [n_items * parts] popcount of the part's words
+};
+
+__device__ __forceinline__ void plan_slice(int n, int parts, int part, int &lo, int &hi)
+{
+    const int per = (n + parts - 1) / parts;
+    lo = min(n, part * per); hi = min(n, lo + per);
+}
+
+// phase A: bit offset of every RLE group; consistency with ref_len / seq_len (status 16 and invalid chunks otherwise)
+__global__ void __launch_bounds__(PLAN_THREADS) plan_groups_kernel(const PlanArgs a)
 {
     __shared__ int s_warp[PLAN_THREADS / 32];
     __shared__ int s_bad;
     const int it = blockIdx.x;
-    if (it >= n_items) return;
-    ItemDesc I = items[it];
-    const uint32_t *g_rle = rle + I.cig_off;
-    int32_t *g_off = grp_off + I.cig_off + it;           // cig_n + 1 entries per item
-    uint32_t *g_bits = bits + I.bit_word_off;
-    uint32_t *g_cum = cum + I.bit_word_off;
+    const ItemDesc I = a.items[it];
+    const uint32_t *g_rle = a.rle + I.cig_off;
+    int32_t *g_off = a.grp_off + I.cig_off + it;         // cig_n + 1 entries per item
     const int P = I.total_ops;
-    const int nwords = (P >> 5) + 1;
     if (threadIdx.x == 0) s_bad = 0;
     __syncthreads();
-
-    // ---- phase A: bit offset of every RLE group; consistency with ref_len / seq_len
     int carry = 0, nD = 0, nI = 0;
     for (int base = 0; base < I.cig_n; base += PLAN_THREADS) {
         const int g = base + threadIdx.x;
@@ -80,59 +91,102 @@ plan_kernel(ItemDesc *items, int n_items, const uint32_t *__restrict__ rle, int3
     __syncthreads();
     const bool bad = s_bad || tD != I.ref_len || tI != I.seq_len || carry != P;
     if (bad) {
-        if (threadIdx.x == 0) items[it].status = 16;      // NPORE_ST_BAD_CIGAR
+        if (threadIdx.x == 0) a.items[it].status = 16;    // NPORE_ST_BAD_CIGAR
         for (int k = threadIdx.x; k < I.n_chunks; k += PLAN_THREADS) {
             ChunkDesc c = {}; c.item = it; c.valid = 0; c.B = 0;
-            chunks[I.chunk_first + k] = c;
+            a.chunks[I.chunk_first + k] = c;
         }
-        return;
     }
-    __threadfence_block();
-    __syncthreads();
+}
 
-    // ---- phase B: bit words + phase C: exclusive prefix of popcounts
-    int ccarry = 0;
-    for (int base = 0; base < nwords; base += PLAN_THREADS) {
-        const int w = base + threadIdx.x;
+// phase B: the bit words of one slice of the item + their popcount
+__global__ void __launch_bounds__(PLAN_THREADS) plan_bits_kernel(const PlanArgs a)
+{
+    __shared__ int s_warp[PLAN_THREADS / 32];
+    const int it = blockIdx.x, part = blockIdx.y;
+    const ItemDesc I = a.items[it];
+    if (I.status) { if (threadIdx.x == 0) a.part_cnt[it * a.parts + part] = 0; return; }
+    const uint32_t *g_rle = a.rle + I.cig_off;
+    const int32_t *g_off = a.grp_off + I.cig_off + it;
+    uint32_t *g_bits = a.bits + I.bit_word_off;
+    const int P = I.total_ops;
+    const int nwords = (P >> 5) + 1;
+    int wlo, whi;
+    plan_slice(nwords, a.parts, part, wlo, whi);
+    int cnt = 0;
+    for (int w = wlo + threadIdx.x; w < whi; w += PLAN_THREADS) {
         uint32_t word = 0;
-        if (w < nwords) {
-            const int lo = w << 5, hi = min(lo + 32, P);
-            if (lo < hi) {
-                int a = 0, b = I.cig_n;                    // last group with g_off <= lo
-                while (b - a > 1) { const int m = (a + b) >> 1; if (g_off[m] <= lo) a = m; else b = m; }
-                int g = a, pos = lo;
-                while (pos < hi) {
-                    const int gs = g_off[g], ge = g_off[g + 1];
-                    const int e = min(ge, hi);
-                    if (e > pos) {
-                        const int op = (int)(g_rle[g] & 15);
-                        const int n = e - pos, sh = pos - lo;
-                        const uint32_t span = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << sh;
-                        if (op == 1) word |= span;
-                        else if (op != 2) {
-                            // D,I,D,I,... starting at gs: odd offsets from gs are 'I'
-                            const uint32_t alt = ((gs - lo) & 1) ? 0x55555555u : 0xaaaaaaaau;
-                            word |= span & alt;
-                        }
-                        pos = e;
+        const int lo = w << 5, hi = min(lo + 32, P);
+        if (lo < hi) {
+            int x = 0, y = I.cig_n;                        // last group with g_off <= lo
+            while (y - x > 1) { const int m = (x + y) >> 1; if (g_off[m] <= lo) x = m; else y = m; }
+            int g = x, pos = lo;
+            while (pos < hi) {
+                const int gs = g_off[g], ge = g_off[g + 1];
+                const int e = min(ge, hi);
+                if (e > pos) {
+                    const int op = (int)(g_rle[g] & 15);
+                    const int n = e - pos, sh = pos - lo;
+                    const uint32_t span = (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << sh;
+                    if (op == 1) word |= span;
+                    else if (op != 2) {
+                        // D,I,D,I,... starting at gs: odd offsets from gs are 'I'
+                        const uint32_t alt = ((gs - lo) & 1) ? 0x55555555u : 0xaaaaaaaau;
+                        word |= span & alt;
                     }
-                    g++;
+                    pos = e;
                 }
+                g++;
             }
-            g_bits[w] = word;
         }
-        int tot;
-        const int ex = plan_block_exscan(__popc(word), s_warp, tot);
-        if (w < nwords) g_cum[w] = (uint32_t)(ccarry + ex);
-        ccarry += tot;
+        g_bits[w] = word;
+        cnt += __popc(word);
     }
-    if (threadIdx.x == 0) { g_bits[nwords] = 0; g_cum[nwords] = (uint32_t)ccarry; }
-    __threadfence_block();
-    __syncthreads();
+    int tot;
+    plan_block_exscan(cnt, s_warp, tot);
+    if (threadIdx.x == 0) {
+        a.part_cnt[it * a.parts + part] = tot;
+        if (part == a.parts - 1) g_bits[nwords] = 0;
+    }
+}
 
-    // ---- phase D: chunk descriptors (get_breaks)
-    const int step = max_b_rows - 1;
-    for (int k = threadIdx.x; k < I.n_chunks; k += PLAN_THREADS) {
+// phase C: exclusive prefix of the popcounts (rank array)
+__global__ void __launch_bounds__(PLAN_THREADS) plan_cum_kernel(const PlanArgs a)
+{
+    __shared__ int s_warp[PLAN_THREADS / 32];
+    const int it = blockIdx.x, part = blockIdx.y;
+    const ItemDesc I = a.items[it];
+    if (I.status) return;
+    const uint32_t *g_bits = a.bits + I.bit_word_off;
+    uint32_t *g_cum = a.cum + I.bit_word_off;
+    const int nwords = (I.total_ops >> 5) + 1;
+    int wlo, whi;
+    plan_slice(nwords, a.parts, part, wlo, whi);
+    int carry = 0;
+    for (int q = 0; q < part; q++) carry += a.part_cnt[it * a.parts + q];
+    for (int base = wlo; base < whi; base += PLAN_THREADS) {
+        const int w = base + threadIdx.x;
+        const int c = w < whi ? __popc(g_bits[w]) : 0;
+        int tot;
+        const int ex = plan_block_exscan(c, s_warp, tot);
+        if (w < whi) g_cum[w] = (uint32_t)(carry + ex);
+        carry += tot;
+    }
+    if (part == a.parts - 1 && threadIdx.x == 0) g_cum[nwords] = (uint32_t)carry;
+}
+
+// phase D: chunk descriptors (get_breaks)
+__global__ void __launch_bounds__(PLAN_THREADS) plan_chunks_kernel(const PlanArgs a)
+{
+    const int it = blockIdx.x;
+    const ItemDesc I = a.items[it];
+    if (I.status) return;
+    const uint32_t *g_bits = a.bits + I.bit_word_off, *g_cum = a.cum + I.bit_word_off;
+    const int P = I.total_ops;
+    const int step = a.max_b_rows - 1;
+    int klo, khi;
+    plan_slice(I.n_chunks, a.parts, blockIdx.y, klo, khi);
+    for (int k = klo + threadIdx.x; k < khi; k += PLAN_THREADS) {
         int brk = k * step, nxt = (k + 1 < I.n_chunks) ? (k + 1) * step : P;
         if (k > 0 && ((g_bits[brk >> 5] >> (brk & 31)) & 1u) && !((g_bits[(brk - 1) >> 5] >> ((brk - 1) & 31)) & 1u)) brk--;
         if (k + 1 < I.n_chunks && ((g_bits[nxt >> 5] >> (nxt & 31)) & 1u) && !((g_bits[(nxt - 1) >> 5] >> ((nxt - 1) & 31)) & 1u)) nxt--;
@@ -144,6 +198,6 @@ plan_kernel(ItemDesc *items, int n_items, const uint32_t *__restrict__ rle, int3
         c.rlen = max(0, min(c1 + 1, I.ref_len) - c.c0);
         c.slen = max(0, min(r1 + 1, I.seq_len) - c.r0);
         c.valid = 1; c.pad[0] = c.pad[1] = 0;
-        chunks[I.chunk_first + k] = c;
+        a.chunks[I.chunk_first + k] = c;
     }
 }
