@@ -312,6 +312,37 @@ def test_c5_whole_contig_haplotypes(tables, golden):
         assert g[:4] == h[:4] and g[4] == want
 
 
+@pytest.mark.parametrize("long_min", [1, 64])
+def test_long_item_standardisation_path(tables, monkeypatch, long_min):
+    """Items with many run-length groups (haplotypes) are standardised by the segment-parallel kernel; NPORE_STD_LONG_MIN
+    forces that path onto ordinary reads and mid-sized haplotypes: same CIGARs as the oracle, expanded and run-length,
+    incl. reads whose INDELs sit densely inside homopolymers (shifts chained through short M groups)."""
+    from npore_b200.engine import Realigner
+    monkeypatch.setenv("NPORE_STD_LONG_MIN", str(long_min))
+    S, NP = tables
+    rng = np.random.default_rng(600 + long_min)
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(260_000, rng)
+    reads = synth.make_reads(ref, 12, 8000, rng, cm, tracts=tr)
+    cases = [(rd[9], rd[7], cig.expand_cigar(rd[5])) for rd in reads]
+    keep = tr[rng.random(len(tr)) < 0.6]
+    seq, cg = synth.make_read(ref, rng, cm, p_ins=0.0, p_sub=0.0005, p_del=0.0, tracts=keep)
+    cases.append((ref, seq, cg))
+    # dense INDELs in a low-complexity stretch: 1-2 base M groups between runs
+    poly = "A" * 40 + "C" + "A" * 30 + "GT" * 25 + "A" * 50
+    noisy, _ = synth.make_read(poly * 6, rng, None, p_ins=0.08, p_sub=0.0, p_del=0.08)
+    cases.append((poly * 6, noisy, _))
+    cases.append(("", "", ""))
+    eng = Realigner(S, NP)
+    refs = [oracle.bases_to_int(c[0]) for c in cases]; seqs = [oracle.bases_to_int(c[1]) for c in cases]
+    exp, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], standardize=True)
+    col, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], standardize=True, collapse=True)
+    for k, c in enumerate(cases):
+        want = oracle.standardize(oracle.align(refs[k], seqs[k], c[2], S, NP), refs[k], seqs[k])
+        assert exp[k] == want and col[k] == oracle.collapse_cigar(want), f"case {k}"
+    eng.close()
+
+
 def test_realign_reads_streams_in_batches(tables, tmp_path):
     """The batch scheduler cuts a lazy read stream into several GPU batches; records stay in input order."""
     from npore_b200 import bam, cfg
