@@ -343,6 +343,34 @@ def test_long_item_standardisation_path(tables, monkeypatch, long_min):
     eng.close()
 
 
+def test_pipelined_realigner_matches_single_context(tables):
+    """Several batches in flight on independent contexts / streams / host threads: same results as one context, whatever
+    the completion order."""
+    from npore_b200.engine import NPORE_OUT_RLE, NPORE_OUT_STANDARDIZE, PackedBatch, PipelinedRealigner, Realigner
+    S, NP = tables
+    rng = np.random.default_rng(77)
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(120_000, rng)
+    batches = []
+    for n, length in ((40, 3000), (3, 30_000), (25, 5000), (1, 200), (60, 1500), (8, 9000)):
+        reads = synth.make_reads(ref, n, length, rng, cm, tracts=tr)
+        batches.append(PackedBatch.from_strings([r[9] for r in reads], [r[7] for r in reads], [r[5] for r in reads]))
+    flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE
+    one = Realigner(S, NP)
+    want = []
+    for b in batches:
+        r = one.align_packed(b, flags, one.new_result(b, flags, pinned=False))
+        want.append((r.ops[:r.ops_off[b.n]].copy(), r.rle[:r.rle_off[b.n]].copy(), r.chunk_scores[:r.score_off[b.n]].copy()))
+    one.close()
+    pipe = PipelinedRealigner(S, NP, n_inflight=3)
+    futs = [pipe.submit(b, flags) for b in batches] + [pipe.submit(b, flags) for b in batches[::-1]]
+    got = [f.result()[0] for f in futs]
+    for (ops, rle, sc), r, b in zip(want + want[::-1], got, batches + batches[::-1]):
+        assert np.array_equal(r.ops[:r.ops_off[b.n]], ops) and np.array_equal(r.rle[:r.rle_off[b.n]], rle)
+        assert np.array_equal(r.chunk_scores[:r.score_off[b.n]], sc) and not r.status[:b.n].any()
+    pipe.close()
+
+
 def test_realign_reads_streams_in_batches(tables, tmp_path):
     """The batch scheduler cuts a lazy read stream into several GPU batches; records stay in input order."""
     from npore_b200 import bam, cfg
