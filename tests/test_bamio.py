@@ -188,6 +188,14 @@ def test_reference_bam_fixture_live(golden):
     by = {r[0]: r for r in golden("golden_sam.json")["reads"]}
     got = list(bamio.get_read_data(bam, fa))
     assert len(got) == 10 and all(list(t) == by[t[0]] for t in got)
+    nb = bamio.NativeBam(bam)                               # the native reader on the reference's own file
+    sel = np.concatenate([s for _, s in bamio.select_reads(nb)])
+    g = nb.gather(sel)
+    for k, t in enumerate(got):
+        assert g["seq_ascii"][g["seq_off"][k]:g["seq_off"][k + 1]].tobytes().decode() == t[7]
+        assert (g["qual_ascii"][g["seq_off"][k]:g["seq_off"][k + 1]].tobytes().decode() if nb.has_qual[sel[k]] else "*") == t[8]
+        assert (int(nb.pos[sel[k]]), int(nb.end[sel[k]]), int(nb.hp[sel[k]]), int(nb.flag[sel[k]])) == (t[3], t[6], t[10], t[1])
+    nb.close()
 
 
 @pytest.mark.gpu

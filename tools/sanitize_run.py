@@ -26,6 +26,7 @@ ref, tr = synth.make_reference_with_tracts(60_000, rng)
 rd = synth.make_reads(ref, 1, 45_000, rng, cm, tracts=tr)[0]
 from npore_b200 import cig
 for r, mb in ((30, 20000), (60, 5000)):
+    os.environ["NPORE_STD_LONG_MIN"] = "8" if r == 30 else "100000"      # segment-parallel standardisation on the first pass
     eng = Realigner(S, NP, max_b_rows=mb, r=r)
     ir, iq = oracle.bases_to_int(rd[9]), oracle.bases_to_int(rd[7])
     o, _, _ = eng.align_many([ir], [iq], [cig.expand_cigar(rd[5])], standardize=True)
