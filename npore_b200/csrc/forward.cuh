@@ -408,7 +408,10 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
                         } else {
                             const int n = (int)(D & 7u);
                             const uint32_t n4 = (uint32_t)n << 2;
-                            const bool eq = ((((cc[k].z ^ rw[k]) >> 8) << (32 - 2 * n)) == 0u);
+                            // match() of aln.pyx:606-607: seq[i-n .. i) against ref[j .. j+n).  The row record carries the 6-mer
+                            // that ENDS at seq[i-1] (its last n codes are the read-side unit), the column record the 6-mer that
+                            // starts at ref[j]
+                            const bool eq = (((((rw[k] >> (12 - 2 * n)) ^ cc[k].z) >> 8) << (32 - 2 * n)) == 0u);
                             const bool start = ((rw[k] >> (25 + n)) & 1u) != 0u;
                             const uint32_t f = (uint32_t)((-n) & (NP_RING - 1)) * (uint32_t)(NC * 16) + dsh + myslot4 + (uint32_t)(k * 4) + (start ? 0u : (uint32_t)(NC * 8));
                             const uint32_t ad = FWD_ADDR(f & (uint32_t)(NC * 128 - 4), wbase);

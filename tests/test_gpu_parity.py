@@ -343,6 +343,22 @@ def test_long_item_standardisation_path(tables, monkeypatch, long_min):
     eng.close()
 
 
+def test_len_on_last_copies_of_a_read_tract(tables, golden, engine_factory):
+    """aln.pyx:606-607 compares seq[i-n .. i) with ref[j .. j+n).  On the last copies of a read tract (inserted units
+    followed by a different base) the unit that FOLLOWS row i is not that unit; a kernel that compares the wrong 6-mer
+    loses LEN candidates there (found by tools/gpu_fuzz_live.py; 1 case in 3,700).  Expected values: compiled reference."""
+    groups = {}
+    for c in golden("len_tail_kats.json"):
+        groups.setdefault((c["r"], c["max_n"]), []).append(c)
+    for (r, max_n), cases in sorted(groups.items()):
+        eng = engine_factory(r=r, max_n=max_n)
+        outs, scores, status = eng.align_many([oracle.bases_to_int(c["ref"]) for c in cases], [oracle.bases_to_int(c["seq"]) for c in cases],
+                                              [c["cigar"] for c in cases])
+        for k, c in enumerate(cases):
+            assert outs[k] == c["out"] and status[k] == 0, f"r={r} max_n={max_n} case {k}"
+            assert np.array_equal(scores[k], np.array(c["scores"], dtype=np.float32)), f"r={r} max_n={max_n} case {k}: score"
+
+
 def test_pipelined_realigner_matches_single_context(tables):
     """Several batches in flight on independent contexts / streams / host threads: same results as one context, whatever
     the completion order."""

@@ -72,6 +72,15 @@ def test_fuzz_golden(tables, golden):
         assert oracle.collapse_cigar(oracle.standardize(out, ir, iq)) == c["std"]
 
 
+def test_len_tail_kats(tables, golden):
+    """LEN on the last copies of a read tract (tests/golden/len_tail_kats.json, reference outputs + chunk scores)."""
+    S, NP = tables
+    for c in golden("len_tail_kats.json"):
+        ir, iq = oracle.bases_to_int(c["ref"]), oracle.bases_to_int(c["seq"])
+        got, sc, st = oracle.align(ir, iq, c["cigar"], S, NP, r=c["r"], max_n=c["max_n"], return_scores=True)
+        assert got == c["out"] and st == 0 and np.array_equal(sc, np.array(c["scores"], dtype=np.float32))
+
+
 def test_plan_matches_chunk_count(tables):
     """get_breaks (aln.pyx:344-358): number of chunks and the 'do not split a DI pair' shift."""
     assert oracle.plan("=" * 30, 30, 30, 20).tolist() == [0, 18, 38, 56, 60]      # breaks at 19k land on 'I' after 'D' -> shifted

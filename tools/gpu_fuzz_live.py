@@ -1,0 +1,67 @@
+"""Fresh seeded differential fuzz (not the committed fixtures): CUDA path vs the C oracle -- op strings, chunk scores,
+standardised + collapsed CIGARs -- over random band radii / window sizes / time-slice lengths, small cases and 1-6 kb reads,
+with the long-item standardisation forced on half of the groups.  usage: python tools/gpu_fuzz_live.py [n_groups] [seed]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle  # noqa: E402
+from npore_b200 import cig, synth  # noqa: E402
+from npore_b200.engine import Realigner  # noqa: E402
+
+
+def main():
+    n_groups = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
+    t = np.load(os.path.join(ROOT, "tests/golden/tables.npz")); S, NP = t["sub_scores"], t["np_scores"]
+    cm = synth.call_length_model(NP)
+    rng = np.random.default_rng(seed)
+    ref, tr = synth.make_reference_with_tracts(300_000, rng)
+    bad = total = chunks = 0
+    fails = []
+    t0 = time.time()
+    for g in range(n_groups):
+        r = int(rng.choice([3, 5, 8, 10, 15, 16, 20, 30, 31, 32, 45, 60, 64, 90, 127]))
+        mb = int(rng.choice([12, 20, 37, 64, 100, 257, 1000, 5000, 20000, 65000]))
+        os.environ["NPORE_RR_SLICE"] = str(int(rng.choice([7, 40, 512, 100000])))
+        os.environ["NPORE_STD_LONG_MIN"] = "1" if g % 2 else "4096"
+        max_n = int(rng.choice([6, 6, 6, 3, 1]))
+        cases = []
+        for _ in range(int(rng.integers(10, 60))):
+            rf, sq, cg, _, _ = synth.fuzz_case(rng, cm)
+            cases.append((rf, sq, cg))
+        if mb >= 257:
+            for rd in synth.make_reads(ref, int(rng.integers(1, 5)), int(rng.integers(1000, 6000)), rng, cm, tracts=tr):
+                cases.append((rd[9], rd[7], cig.expand_cigar(rd[5])))
+        eng = Realigner(S, NP, max_b_rows=mb, r=r, max_n=max_n)
+        refs = [oracle.bases_to_int(c[0]) for c in cases]; seqs = [oracle.bases_to_int(c[1]) for c in cases]
+        outs, scores, status = eng.align_many(refs, seqs, [c[2] for c in cases])
+        std, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], standardize=True, collapse=True)
+        for k, c in enumerate(cases):
+            want, wsc, wst = oracle.align(refs[k], seqs[k], c[2], S, NP, max_b_rows=mb, r=r, max_n=max_n, return_scores=True)
+            ws = oracle.collapse_cigar(oracle.standardize(want, refs[k], seqs[k]))
+            ok = outs[k] == want and status[k] == wst and np.array_equal(scores[k], np.asarray(wsc, np.float32)) and std[k] == ws
+            total += 1; chunks += len(wsc); bad += (not ok)
+            if not ok:
+                what = [n for n, f in (("ops", outs[k] != want), ("status", status[k] != wst), ("scores", not np.array_equal(scores[k], np.asarray(wsc, np.float32))),
+                                       ("std", std[k] != ws)) if f]
+                print(f"MISMATCH group {g} case {k}: r={r} mb={mb} max_n={max_n} slice={os.environ['NPORE_RR_SLICE']} "
+                      f"long_min={os.environ['NPORE_STD_LONG_MIN']} len={len(c[0])}/{len(c[1])} differs: {what} status={status[k]}/{wst}", flush=True)
+                fails.append({"ref": c[0], "seq": c[1], "cigar": c[2], "r": r, "mb": mb, "max_n": max_n, "slice": os.environ["NPORE_RR_SLICE"],
+                              "long_min": os.environ["NPORE_STD_LONG_MIN"], "got_ops": outs[k], "want_ops": want, "got_std": std[k], "want_std": ws,
+                              "got_scores": [float(x) for x in scores[k]], "want_scores": [float(x) for x in wsc], "n_in_group": len(cases), "k": k})
+        eng.close()
+    if fails:
+        import json
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(fails, open(os.path.join(ROOT, "gpurun_out", f"fuzz_fail_{seed}.json"), "w"))
+    print(f"live fuzz seed {seed}: {n_groups} groups, {total} cases, {chunks} chunks, {bad} mismatches, {time.time() - t0:.0f} s")
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main() else 0)
