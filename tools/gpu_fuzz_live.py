@@ -1,6 +1,6 @@
 """Fresh seeded differential fuzz (not the committed fixtures): CUDA path vs the C oracle -- op strings, chunk scores,
 standardised + collapsed CIGARs -- over random band radii / window sizes / time-slice lengths, small cases and 1-6 kb reads,
-with the long-item standardisation forced on half of the groups.  usage: python tools/gpu_fuzz_live.py [n_groups] [seed]"""
+with the long-item standardisation forced on half of the groups.  usage: python tools/gpu_fuzz_live.py [n_groups] [seed] [n_production_reads]"""
 import os
 import sys
 import time
@@ -34,6 +34,24 @@ def main():
         for _ in range(int(rng.integers(10, 60))):
             rf, sq, cg, _, _ = synth.fuzz_case(rng, cm)
             cases.append((rf, sq, cg))
+        for _ in range(int(rng.integers(5, 30))):       # tract-centred: unit of 1-6 bases, 3-140 copies, copy-number change + noise
+            alpha = list("ACGT") if rng.random() < 0.8 else list("ACGTN")
+            unit = "".join(rng.choice(list("ACGT"), size=int(rng.integers(1, 7))))
+            copies = int(rng.integers(3, max(4, 140 // len(unit))))
+            pre = "".join(rng.choice(alpha, size=int(rng.integers(0, 30)))); suf = "".join(rng.choice(alpha, size=int(rng.integers(0, 30))))
+            rf = pre + unit * copies + suf
+            sq0 = pre + unit * int(rng.integers(max(0, copies - 12), copies + 12)) + suf
+            sq, _ = synth.make_read(sq0, rng, None, p_ins=0.03, p_sub=0.03, p_del=0.03, alphabet="".join(alpha)) if sq0 else ("", "")
+            m = min(len(rf), len(sq))
+            style = rng.random()
+            if style < 0.5:
+                cg = "M" * m + "D" * (len(rf) - m) + "I" * (len(sq) - m)
+            elif style < 0.75:
+                cg = "D" * (len(rf) - m) + "I" * (len(sq) - m) + "M" * m
+            else:
+                h = m // 2
+                cg = "=" * h + "I" * (len(sq) - m) + "D" * (len(rf) - m) + "X" * (m - h)
+            cases.append((rf, sq, cg))
         if mb >= 257:
             for rd in synth.make_reads(ref, int(rng.integers(1, 5)), int(rng.integers(1000, 6000)), rng, cm, tracts=tr):
                 cases.append((rd[9], rd[7], cig.expand_cigar(rd[5])))
@@ -59,6 +77,24 @@ def main():
         import json
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(fails, open(os.path.join(ROOT, "gpurun_out", f"fuzz_fail_{seed}.json"), "w"))
+    n_reads = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    if n_reads:        # production-style reads (learned copy-number error model) at align()'s defaults, one GPU batch
+        for k in ("NPORE_RR_SLICE", "NPORE_STD_LONG_MIN"):
+            os.environ.pop(k, None)
+        reads = synth.make_reads(ref, n_reads, int(rng.integers(2000, 6000)), rng, cm, tracts=tr)
+        eng = Realigner(S, NP)
+        refs = [oracle.bases_to_int(r[9]) for r in reads]; seqs = [oracle.bases_to_int(r[7]) for r in reads]
+        cgs = [cig.expand_cigar(r[5]) for r in reads]
+        outs, scores, status = eng.align_many(refs, seqs, cgs)
+        std, _, _ = eng.align_many(refs, seqs, cgs, standardize=True, collapse=True)
+        for k in range(n_reads):
+            want, wsc, wst = oracle.align(refs[k], seqs[k], cgs[k], S, NP, return_scores=True)
+            ok = outs[k] == want and status[k] == wst and np.array_equal(scores[k], np.asarray(wsc, np.float32)) and \
+                std[k] == oracle.collapse_cigar(oracle.standardize(want, refs[k], seqs[k]))
+            total += 1; chunks += len(wsc); bad += (not ok)
+            if not ok:
+                print(f"MISMATCH production read {k}", flush=True)
+        eng.close()
     print(f"live fuzz seed {seed}: {n_groups} groups, {total} cases, {chunks} chunks, {bad} mismatches, {time.time() - t0:.0f} s")
     return bad
 
