@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 OPS_PER_CU = 28
 BYTES_PER_CU = 2         # packed (TYP,RUN) traceback record
-NCU_DRAM_BYTES_PER_LAUNCH = 9.715e9   # forward_kernel<2> on the C2 batch: 8.844 GB written + 0.871 GB read (ncu, profiles/r01_final_*)
+NCU_DRAM_BYTES_PER_LAUNCH = 8.659e9   # forward_kernel<2> on the C2 batch: 7.968 GB written + 0.691 GB read (ncu, profiles/r01_final_*)
 
 
 def load_tables():
