@@ -524,12 +524,14 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
             int long_min = 4096;
             if (const char *e = getenv("NPORE_STD_LONG_MIN")) long_min = std::max(1, atoi(e));
             const bool any_long = max_ops >= long_min;              // an item cannot have more groups than ops
-            standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa, any_long ? long_min : 0x7fffffff);
-            CU(cudaGetLastError()); S.launches++;
+            // the long-item kernel goes first and marks its items (rle_which = 1); the per-warp kernel takes what is left.
+            // (Both look at the group count BEFORE standardisation: the sweeps change it.)
             if (any_long) {
                 standardize_long_kernel<<<n, FIN_WIDE, 0, ctx->stream>>>(fa, long_min);
                 CU(cudaGetLastError()); S.launches++;
             }
+            standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa, long_min);
+            CU(cudaGetLastError()); S.launches++;
             if (want_ops) {
                 if (parts > 1) { expand_count_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa); S.launches++; }
                 expand_fill_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa);

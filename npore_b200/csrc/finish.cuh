@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(FIN_THREADS) standardize_kernel(const FinishAr
 {
     const int it = blockIdx.x * (FIN_THREADS / 32) + (threadIdx.x >> 5);
     if (it >= a.n_items) return;
-    if (a.rle_len[it] >= long_min_groups) return;                 // standardize_long_kernel's
+    if (a.rle_which[it] != 0) return;                             // already standardised by standardize_long_kernel (launched first)
+    (void)long_min_groups;
     const bool lead = (threadIdx.x & 31) == 0;
     const ItemDesc &I = a.items[it];
     uint32_t *A = a.rleA + I.out_off, *B = a.rleB + I.out_off;

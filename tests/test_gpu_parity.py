@@ -337,9 +337,24 @@ def test_long_item_standardisation_path(tables, monkeypatch, long_min):
     refs = [oracle.bases_to_int(c[0]) for c in cases]; seqs = [oracle.bases_to_int(c[1]) for c in cases]
     exp, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], standardize=True)
     col, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], standardize=True, collapse=True)
+    wants = []
     for k, c in enumerate(cases):
-        want = oracle.standardize(oracle.align(refs[k], seqs[k], c[2], S, NP), refs[k], seqs[k])
+        aligned = oracle.align(refs[k], seqs[k], c[2], S, NP)
+        want = oracle.standardize(aligned, refs[k], seqs[k])
+        wants.append((aligned, want))
         assert exp[k] == want and col[k] == oracle.collapse_cigar(want), f"case {k}"
+    # the split between the two kernels is decided on the group count BEFORE standardisation (the sweeps change it): items
+    # whose count crosses the threshold during the sweeps must be standardised exactly once
+    crossed = 0
+    for k, (aligned, want) in enumerate(wants):
+        ngroups = lambda ops: sum(1 for a, b in zip(ops, ops[1:]) if a != b) + (1 if ops else 0)   # noqa: E731
+        m0, m1 = ngroups(aligned.replace("=", "M").replace("X", "M")), ngroups(want)
+        if m1 > m0 > 0:
+            crossed += 1
+            monkeypatch.setenv("NPORE_STD_LONG_MIN", str(m0 + 1))
+            one, _, _ = eng.align_many([refs[k]], [seqs[k]], [cases[k][2]], standardize=True, collapse=True)
+            assert one[0] == oracle.collapse_cigar(want), f"case {k} at threshold {m0 + 1}"
+    assert crossed > 0 or long_min != 1
     eng.close()
 
 
