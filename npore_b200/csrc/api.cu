@@ -530,7 +530,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
                 standardize_long_kernel<<<n, FIN_WIDE, 0, ctx->stream>>>(fa, long_min);
                 CU(cudaGetLastError()); S.launches++;
             }
-            standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa, long_min);
+            standardize_kernel<<<(n + FIN_THREADS / 32 - 1) / (FIN_THREADS / 32), FIN_THREADS, 0, ctx->stream>>>(fa);
             CU(cudaGetLastError()); S.launches++;
             if (want_ops) {
                 if (parts > 1) { expand_count_kernel<<<grid_np, FIN_WIDE, 0, ctx->stream>>>(fa); S.launches++; }

@@ -285,12 +285,11 @@ __device__ __forceinline__ int rle_id_to_m(const uint32_t *in, int m, uint32_t *
 // one item per WARP: lane 0 does the sweeps (32 different sequential sweeps inside one warp would serialise), all lanes
 // prepare the base comparisons of the two push_indels_left sweeps.  The comparison results go to the upper half of the
 // input buffer's item region (capacity Lref+Lseq words, of which the groups use the first m).
-__global__ void __launch_bounds__(FIN_THREADS) standardize_kernel(const FinishArgs a, int long_min_groups)
+__global__ void __launch_bounds__(FIN_THREADS) standardize_kernel(const FinishArgs a)
 {
     const int it = blockIdx.x * (FIN_THREADS / 32) + (threadIdx.x >> 5);
     if (it >= a.n_items) return;
     if (a.rle_which[it] != 0) return;                             // already standardised by standardize_long_kernel (launched first)
-    (void)long_min_groups;
     const bool lead = (threadIdx.x & 31) == 0;
     const ItemDesc &I = a.items[it];
     uint32_t *A = a.rleA + I.out_off, *B = a.rleB + I.out_off;
