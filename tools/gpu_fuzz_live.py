@@ -63,10 +63,13 @@ def main():
         refs = [oracle.bases_to_int(c[0]) for c in cases]; seqs = [oracle.bases_to_int(c[1]) for c in cases]
         outs, scores, status = eng.align_many(refs, seqs, [c[2] for c in cases])
         std, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], standardize=True, collapse=True)
+        raw_rle, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], collapse=True)            # '=XID' run-length, not standardised
+        exp_std, _, _ = eng.align_many(refs, seqs, [c[2] for c in cases], standardize=True)          # expanded 'MID'
         for k, c in enumerate(cases):
             want, wsc, wst = oracle.align(refs[k], seqs[k], c[2], S, NPg, gopen, gext, max_b_rows=mb, r=r, max_n=max_n, max_l=max_l, return_scores=True)
             ws = oracle.collapse_cigar(oracle.standardize(want, refs[k], seqs[k]))
             ok = outs[k] == want and status[k] == wst and np.array_equal(scores[k], np.asarray(wsc, np.float32)) and std[k] == ws
+            ok = ok and raw_rle[k] == oracle.collapse_cigar(want) and oracle.collapse_cigar(exp_std[k]) == ws
             total += 1; chunks += len(wsc); bad += (not ok)
             if not ok:
                 what = [n for n, f in (("ops", outs[k] != want), ("status", status[k] != wst), ("scores", not np.array_equal(scores[k], np.asarray(wsc, np.float32))),
