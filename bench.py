@@ -211,9 +211,17 @@ def cpu_baseline(reads, budget_reads_per_core=16):
         dt = cpu_port_run(sample)
         kind, used = "port", 1
     cu = n_cu_of(sample)
-    return {"value": cu / dt / 1e9, "unit": "GCUPS", "cores": used, "kind": kind, "reads_per_s": len(sample) / dt,
-            "sample": f"first {len(sample)} reads of the workload ({cu/1e9:.3f} GCU), wall {dt:.2f} s, "
-                      + ("mp.Pool(imap_unordered, realign_read) over all host cores" if kind == "reference" else "1 thread, C port")}
+    out = {"value": cu / dt / 1e9, "unit": "GCUPS", "cores": used, "kind": kind, "reads_per_s": len(sample) / dt,
+           "sample": f"first {len(sample)} reads of the workload ({cu/1e9:.3f} GCU), wall {dt:.2f} s, "
+                     + ("mp.Pool(imap_unordered, realign_read) over all host cores" if kind == "reference" else "1 thread, C port")}
+    if have_ref:         # also the 1-process figure (a Pool of one worker, 6 reads)
+        try:
+            one = sample[:6]
+            d1 = cpu_reference_run(one, 1)
+            out["one_process"] = {"value": n_cu_of(one) / d1 / 1e9, "unit": "GCUPS", "reads_per_s": len(one) / d1}
+        except Exception as e:      # noqa: BLE001
+            out["one_process"] = {"unavailable": repr(e)}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ main
