@@ -16,15 +16,17 @@
 //                      LENmask<<22 (bit n-1: raw[j][n] has L!=0 && L_IDX==0).  "Relaid" = the record of column j
 //                      holds what the SHR gather of a cell in column j needs from columns j-1..j-6.  Only the
 //                      rare generic path of the forward kernel reads it.
-//   colrec[j] (uint4): .x/.y = the first two SHR candidate descriptors of column j, period n descending (0 = none):
-//                        [0:2] n  [3:9] L  [10:19] score-table row (n-1)*T + min(L, clamp) (only when NC <= 128)
-//                        [20:31] (NC <= 128; [19:31] for NC = 256) (byte offset of the source cell in the forward
-//                        kernel's history ring)>>2 = ring row (-n mod 8), array (0 = MAT value if the source column
-//                        starts the tract, L_IDX==0; 1 = carried SHR run-start value otherwise), slot (j-n) mod NC
-//                      .z = [0] generic path (more than two SHR candidates or more than one LEN-eligible period; then
-//                           .x/.y/.w are 0)  [1] k-mer contains N  [2:4] base ref[j-1]  [8:19] 2-bit k-mer ref[j..j+5]
-//                      .w = LEN descriptor of the single LEN-eligible period at j: [0:2] n  [3:9] L  [10:19] table row
-//                           [20:25] one-hot period mask aligned with rowrec's "tract present" bits (bit 19+n)
+//   colrec[2j], colrec[2j+1] (2 x uint4): {S0.A, S0.B, S0.C, S1.A}, {S1.B, S1.C, Z, LEN}
+//     S0 / S1 = the first two SHR candidate descriptors of column j, period n descending:
+//        A [31:19] (byte offset of the source pair in the forward kernel's history ring) >> 3: ring row (-n mod 8), position of
+//                  slot (j-n) mod NC in the row, pair {MAT.VAL, -} if the source column starts the tract (L_IDX==0) else
+//                  {carried SHR run-start value, runs}      [18:16] n      [15:0] score-table row (n-1)*(max_l+1) + L
+//        B ceil(65536 / n)         C 0 if the source column starts the tract, else 0xffff0000
+//        "no candidate": A = the index of the +INF table row, B = C = 0
+//     Z   = [0] generic path (more than two SHR candidates or more than one LEN-eligible period; then S0/S1/LEN are empty)
+//           [1] k-mer contains N  [2:4] base ref[j-1]  [8:19] 2-bit k-mer ref[j..j+5]
+//     LEN = descriptor of the single LEN-eligible period at j: [0:2] n  [3:12] table row  [20:25] one-hot period mask
+//           aligned with rowrec's "tract present" bits (bit 19+n)
 //   rowrec[i] (uint32): [4] k-mer contains N  [5:7] base seq[i-1]  [8:19] 2-bit k-mer seq[i-6..i-1] (the LEN unit
 //                       seq[i-n..i) is its last n codes)
 //                       [20:25] tract present at i-n (bit 19+n)  [26:31] tract start at i-n (bit 25+n, L_IDX==0)
@@ -42,7 +44,7 @@ struct AnnotateArgs {
     const uint8_t *ref_codes, *seq_codes;
     uint8_t *raw_ref, *raw_seq;    // 8 B per entry
     uint4 *colrec; uint2 *relaid; uint32_t *rowrec;
-    int max_n, max_l, nc, np_dim, np_clamp, inf_row;
+    int max_n, max_l, nc, inf_row;      // inf_row = max_n * (max_l + 1)
 };
 
 // np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
@@ -191,16 +193,13 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         const uint8_t *s = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
         uint8_t *raw = a.raw_ref + sl.col_off * 8;
         annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr);
-        uint4 *out = a.colrec + sl.col_off;
+        uint4 *out = a.colrec + 2 * sl.col_off;
         uint2 *rel = a.relaid + sl.col_off;
-        const int NC = a.nc;
+        const int NC = a.nc, CPL = NC / 32;
         for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
             uint2 v = make_uint2(0u, 0u);
-            // "no candidate" SHR descriptor (NC <= 128): table row = the all-INF row, so the candidate can never win
-            // (its ring offset addresses the previous anti-diagonal's row, slot 0: a location nobody writes during the step)
-            const uint32_t empty_f = (uint32_t)((NP_RING - 1) * NC * 16) >> 2;
-            const uint32_t empty = NC <= 128 ? (((uint32_t)a.inf_row << 10) | (empty_f << 20)) : (empty_f << 19);
-            uint4 w = make_uint4(empty, empty, 0u, 0u);
+            const uint32_t empty = (uint32_t)a.inf_row;       // "no candidate": the all-INF table row; the source it reads is irrelevant
+            uint32_t sA[2] = {empty, empty}, sB[2] = {0u, 0u}, sC[2] = {0u, 0u}, z = 0u, lenw = 0u;
             if (j < len + 8) {
                 uint32_t lenm = 0, nshr = 0, nlen = 0;
 #pragma unroll
@@ -209,19 +208,22 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                     if (n <= 4) v.x |= b << (8 * (n - 1)); else v.y |= b << (8 * (n - 5));
                     const uint32_t L = b & 0x7fu;
                     if (L) {
-                        // byte offset inside one warp's ring [NP_RING][4 arrays][NC] floats
-                        const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (NC * 16) + ((b & 0x80u) ? 0u : (uint32_t)(NC * 4)) +
-                                           (uint32_t)((j - n) & (NC - 1)) * 4u;
-                        const uint32_t trow = (uint32_t)((n - 1) * a.np_dim + min((int)L, a.np_clamp));
-                        const uint32_t d = (uint32_t)n | (L << 3) | (NC <= 128 ? (trow << 10) | ((F >> 2) << 20) : ((F >> 2) << 19));
-                        if (nshr == 0) w.x = d; else if (nshr == 1) w.y = d;
+                        // byte offset inside one warp's ring [NP_RING rows][NC positions][16 B]; slot s sits at position
+                        // (s % CPL)*32 + s / CPL; pair 0 = {MAT.VAL, -}, pair 1 = {SHR run-start value, runs}
+                        const uint32_t ss = (uint32_t)(j - n) & (uint32_t)(NC - 1);
+                        const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (uint32_t)(NC * 16) + ((ss % CPL) * 32u + ss / CPL) * 16u + ((b & 0x80u) ? 0u : 8u);
+                        if (nshr < 2) {
+                            sA[nshr] = ((F | (uint32_t)n) << 16) | (uint32_t)((n - 1) * (a.max_l + 1) + (int)L);
+                            sB[nshr] = (65536u + (uint32_t)n - 1u) / (uint32_t)n;
+                            sC[nshr] = (b & 0x80u) ? 0u : 0xffff0000u;
+                        }
                         nshr++;
                     }
                     const uint32_t o = raw_byte(raw, len, j, n);
                     if ((o & 0x7fu) && (o & 0x80u)) {
                         lenm |= 1u << (n - 1);
                         const uint32_t Lo = o & 0x7fu;
-                        w.w = (uint32_t)n | (Lo << 3) | ((uint32_t)((n - 1) * a.np_dim + min((int)Lo, a.np_clamp)) << 10) | (1u << (19 + n));
+                        lenw = (uint32_t)n | ((uint32_t)((n - 1) * (a.max_l + 1) + (int)Lo) << 3) | (1u << (19 + n));
                         nlen++;
                     }
                 }
@@ -230,10 +232,11 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                 uint32_t hasN = 0;
                 const uint32_t km = kmer2_of(s, len, j, hasN);
                 const bool more = nshr > 2 || nlen > 1;
-                if (more) { w.x = w.y = empty; w.w = 0u; }
-                w.z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (km << 8);
+                if (more) { sA[0] = sA[1] = empty; sB[0] = sB[1] = sC[0] = sC[1] = 0u; lenw = 0u; }
+                z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (km << 8);
             }
-            out[j] = w;
+            out[2 * j] = make_uint4(sA[0], sB[0], sC[0], sA[1]);
+            out[2 * j + 1] = make_uint4(sB[1], sC[1], z, lenw);
             rel[j] = v;
         }
     } else {

@@ -123,19 +123,24 @@ template <int CPL>
 int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 {
     constexpr int WARPS = fwd_warps(CPL);
-    // rings are aligned to their size inside the CTA's shared window; the window starts 1 KB in (reserved) + the static
-    // arrays, so (ring - 1 KB) of slack always suffices -- a full extra ring would push 4 CTAs over the 164 KB carve-out
-    constexpr size_t RING = (size_t)4 * NP_RING * 32 * CPL * sizeof(float);
-    const size_t smem = (size_t)WARPS * RING + (FWD_ALIGNED ? RING - 1024 : 0);
+    // rings are aligned to their size inside the CTA's shared window (cell address = offset | base).  The dynamic window
+    // starts after the per-CTA reservation and the kernel's static arrays, so the slack needed is known exactly; the kernel
+    // re-derives it from the real addresses and raises ctl[3] instead of running past the window.
+    constexpr size_t RING = (size_t)NP_RING * 32 * CPL * 16;
+    cudaFuncAttributes fattr;
+    CU(cudaFuncGetAttributes(&fattr, forward_kernel<CPL>));
+    int reserved = 1024;
+    cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device);
+    const size_t start = (size_t)reserved + fattr.sharedSizeBytes;
+    const size_t slack = (RING - start % RING) % RING;
+    const size_t smem = (size_t)WARPS * RING + slack;
     CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     {   // ask for the smallest shared-memory carve-out that holds the resident CTAs: the rest of the 256 KB is L1 for the
         // score-table lookups (the default picked 196 KB where 164 KB is enough, leaving 56 instead of 92 KB of L1)
-        cudaFuncAttributes fattr;
-        CU(cudaFuncGetAttributes(&fattr, forward_kernel<CPL>));
-        const size_t need = (size_t)per_sm * (smem + fattr.sharedSizeBytes + 1024);
+        const size_t need = (size_t)per_sm * (smem + fattr.sharedSizeBytes + reserved);
         int pct = (int)((need * 100 + 233472 - 1) / 233472);
         if (pct > 100) pct = 100;
         CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
@@ -180,7 +185,6 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     if (max_l < 1 || max_l > 127 || np_dim < max_l) return NPORE_ERR_BAD_ARG;   // L must fit 7 bits; index clamp is max_l-1
     if (max_b_rows < 2 || max_b_rows > 65000) return NPORE_ERR_BAD_ARG;          // runs are carried in 16 bits
     if (r < 1 || 2 * r + 1 > 32 * 8) return NPORE_ERR_BAD_ARG;
-    if ((int64_t)np_n * np_dim > 1023) return NPORE_ERR_BAD_ARG;                 // score-table row index is a 10-bit descriptor field
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return NPORE_ERR_NO_DEVICE; }
     if (device < 0 || device >= ndev) return NPORE_ERR_BAD_ARG;
@@ -194,27 +198,37 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(NPORE_ERR_CUDA);
     for (auto &e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) return bail(NPORE_ERR_CUDA);
     ctx->P.r = r; ctx->P.W = 2 * r + 1; ctx->P.max_n = max_n; ctx->P.max_l = max_l; ctx->P.max_b_rows = max_b_rows;
-    ctx->P.np_dim = np_dim; ctx->P.np_clamp = max_l - 1; ctx->P.np_rows = np_n * np_dim;
+    ctx->P.np_dim = np_dim; ctx->P.np_clamp = max_l - 1; ctx->P.np_rows = max_n * (max_l + 1);
     ctx->P.gap_open = indel_start; ctx->P.gap_ext = indel_extend;
     ctx->np_n = np_n;
     const int W = 2 * r + 1;
     ctx->cpl = W <= 32 ? 1 : W <= 64 ? 2 : W <= 128 ? 4 : 8;
     ctx->tbs = np_tbs(ctx->cpl);
     if (ctx->d_sub.ensure(25 * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
-    // score table re-laid with a guard column: np2[row][c] = np_scores[row][c-1], np2[row][0] = 100.0 (forward.cuh)
-    std::vector<float> np2((size_t)(np_n * np_dim + 1) * (np_dim + 1), __builtin_inff());   // + one all-INF row: "no candidate"
-    for (int64_t row = 0; row < (int64_t)np_n * np_dim; row++) {
-        np2[(size_t)row * (np_dim + 1)] = 100.0f;
-        memcpy(&np2[(size_t)row * (np_dim + 1) + 1], np_scores + row * np_dim, sizeof(float) * (size_t)np_dim);
+    // score tables re-laid per (period n, tract length L) so that a candidate is one load (forward.cuh): row (n-1)*(max_l+1)+L,
+    //   tabS[row][q] = np_score(n, L, -(q+1))   (SHR after q = trunc(run/n) units already removed)
+    //   tabL[row][q] = np_score(n, L, +(q+1))   (LEN likewise)
+    // with np_score exactly as the reference CALLS it (aln.pyx:257-274 with max_l in the max_n slot, :615): 100.0 if
+    // L + indel < 0, else np_scores[n-1][min(L, max_l-1)][min(L + indel, max_l-1)].  Row `rows` is all +INF ("no candidate").
+    {
+        const int rows = max_n * (max_l + 1), clampv = max_l - 1;
+        std::vector<float> tab((size_t)2 * (rows + 1) * NP_TABQ, __builtin_inff());
+        for (int sgn = 0; sgn < 2; sgn++)
+            for (int n = 1; n <= max_n; n++)
+                for (int L = 0; L <= max_l; L++)
+                    for (int q = 0; q < NP_TABQ; q++) {
+                        const int call = sgn ? L + q + 1 : L - q - 1;
+                        float v = 100.0f;
+                        if (call >= 0) v = np_scores[((size_t)(n - 1) * np_dim + std::min(L, clampv)) * np_dim + std::min(call, clampv)];
+                        tab[((size_t)sgn * (rows + 1) + (size_t)(n - 1) * (max_l + 1) + L) * NP_TABQ + q] = v;
+                    }
+        if (ctx->d_np.ensure(tab.size() * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
+        if (cudaMemcpy(ctx->d_np.p, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NPORE_ERR_CUDA);
     }
-    if (ctx->d_np.ensure(np2.size() * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
     if (cudaMemcpy(ctx->d_sub.p, sub_scores, 25 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NPORE_ERR_CUDA);
-    if (cudaMemcpy(ctx->d_np.p, np2.data(), np2.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess)
-        return bail(NPORE_ERR_CUDA);
     if (ctx->d_counter.ensure(64) != cudaSuccess) return bail(NPORE_ERR_OOM);
     size_t fr = 0, tot = 0;
     cudaMemGetInfo(&fr, &tot);
-    fwd_init_constants();
     if (cudaGetLastError() != cudaSuccess) return bail(NPORE_ERR_CUDA);
     ctx->scratch_budget = (size_t)((double)fr * 0.55);
     if (const char *s = getenv("NPORE_SCRATCH_MB")) ctx->scratch_budget = (size_t)atoll(s) << 20;
@@ -378,7 +392,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     ctx->subs.clear();
     size_t max_col = 0, max_row = 0, max_tb = 0;
     {
-        const size_t per_entry = 16 + 8 + 8 + 4 + 8;   // colrec, relaid, raw_ref, rowrec, raw_seq
+        const size_t per_entry = 32 + 8 + 8 + 4 + 8;   // colrec, relaid, raw_ref, rowrec, raw_seq
         size_t col = 0, row = 0, tb = 0; int first = 0;
         for (int64_t k = 0; k < nchunks; k++) {
             const int bm = ctx->chunk_bmax[ctx->order[k]];
@@ -399,7 +413,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
             max_col = std::max(max_col, col); max_row = std::max(max_row, row); max_tb = std::max(max_tb, tb);
         }
     }
-    CU(ctx->d_colrec.ensure(max_col * 16 + 64)); CU(ctx->d_relaid.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
+    CU(ctx->d_colrec.ensure(max_col * 32 + 64)); CU(ctx->d_relaid.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
     CU(ctx->d_rowrec.ensure(max_row * 4 + 64)); CU(ctx->d_raw_seq.ensure(max_row * 8 + 64));
     CU(ctx->d_tb.ensure(max_tb * (size_t)(64 * ctx->tbs) + 256));
     int max_sub = 1;
@@ -411,6 +425,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     CU(ctx->d_rr_state.ensure(sizeof(uint32_t) * fwd_rr_state_words(ctx->cpl) * (size_t)max_sub));
     if (nchunks) CU(cudaMemcpyAsync(ctx->d_slots.p, ctx->slots.data(), sizeof(ChunkSlot) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
 
+    CU(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));      // forward-kernel error flag
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     // ---- plan
     int max_ops = 1;
@@ -443,8 +458,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         aa.ref_codes = ctx->d_ref.as<uint8_t>(); aa.seq_codes = ctx->d_seq.as<uint8_t>();
         aa.raw_ref = ctx->d_raw_ref.as<uint8_t>(); aa.raw_seq = ctx->d_raw_seq.as<uint8_t>();
         aa.colrec = ctx->d_colrec.as<uint4>(); aa.relaid = ctx->d_relaid.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
-        aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.np_dim = ctx->P.np_dim; aa.np_clamp = ctx->P.np_clamp;
-        aa.inf_row = ctx->np_n * ctx->P.np_dim;
+        aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.inf_row = ctx->P.np_rows;
         CU(cudaEventRecord(e0, ctx->stream));
         annotate_kernel<<<2 * sb.count, ANN_THREADS, 0, ctx->stream>>>(aa);
         CU(cudaGetLastError()); S.launches++;
@@ -452,19 +466,16 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
 
         ForwardArgs fa{};
         fa.chunks = aa.chunks; fa.slots = aa.slots; fa.order = aa.order; fa.n = sb.count;
-        fa.counter = ctx->d_counter.as<int>(); fa.items = aa.items; fa.bits = ctx->d_bits.as<uint32_t>();
+        fa.items = aa.items; fa.bits = ctx->d_bits.as<uint32_t>(); fa.err = ctx->d_counter.as<int>();
         fa.ref_codes = aa.ref_codes; fa.seq_codes = aa.seq_codes; fa.colrec = aa.colrec; fa.relaid = aa.relaid; fa.rowrec = aa.rowrec;
-        fa.tb = ctx->d_tb.as<uint16_t>(); fa.np_tab = ctx->d_np.as<float>(); fa.sub_tab = ctx->d_sub.as<float>();
+        fa.tb = ctx->d_tb.as<uint16_t>(); fa.tab = ctx->d_np.as<float>(); fa.sub_tab = ctx->d_sub.as<float>();
         fa.out = ctx->d_chunk_out.as<ChunkOut>();
         fa.P = ctx->P;
         fa.rr_q = ctx->d_rr_q.as<int>(); fa.rr_mask = rr_cap - 1; fa.rr_ctl = ctx->d_rr_ctl.as<int>();
         fa.rr_state = ctx->d_rr_state.as<uint32_t>(); fa.rr_slice = ctx->rr_slice;
-#if FWD_RR
         CU(cudaMemsetAsync(ctx->d_rr_state.p, 0, sizeof(uint32_t) * fwd_rr_state_words(ctx->cpl) * (size_t)sb.count, ctx->stream));
         rr_init_kernel<<<64, 256, 0, ctx->stream>>>(fa.rr_q, rr_cap, sb.count, fa.rr_ctl);
         CU(cudaGetLastError()); S.launches++;
-#endif
-        CU(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));
         int rc = NPORE_OK;
         switch (ctx->cpl) {
         case 1: rc = launch_forward<1>(ctx, fa, sb.count); break;
@@ -489,7 +500,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     // ---- finish
     cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5];
     CU(cudaEventRecord(e0, ctx->stream));
-    const size_t small_bytes = (size_t)n * 12 + (size_t)ctx->n_chunks * sizeof(ChunkOut) + 64;
+    const size_t small_bytes = (size_t)n * 12 + (size_t)ctx->n_chunks * sizeof(ChunkOut) + 64;      // + the error flag in the last 4 bytes
     CU(ctx->h_small.ensure(small_bytes));
     if (n) {
         FinishArgs fa{};
@@ -552,8 +563,12 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         CU(cudaMemcpyAsync(h_rlen, ctx->d_rle_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->n_chunks) CU(cudaMemcpyAsync(h_co, ctx->d_chunk_out.p, sizeof(ChunkOut) * (size_t)ctx->n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
     }
+    int *h_err = reinterpret_cast<int *>(static_cast<char *>(ctx->h_small.p) + small_bytes - 4);
+    *h_err = 0;
+    CU(cudaMemcpyAsync(h_err, ctx->d_counter.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    if (*h_err) return fail(ctx, NPORE_ERR_CUDA, "forward kernel: shared-memory window smaller than the history rings");
     for (size_t si = 0; si < ctx->subs.size(); si++) {
         float t;
         cudaEventElapsedTime(&t, ctx->sub_ev[4 * si], ctx->sub_ev[4 * si + 1]); ms_ann += t;
@@ -565,9 +580,6 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     cudaEventElapsedTime(&S.ms_kernels_total, ctx->ev[2], e1);
     S.ms_annotate = ms_ann; S.ms_forward = ms_fwd; S.ms_traceback = ms_tb;
     S.n_sub_batches = (int)ctx->subs.size();
-#ifdef FWD_SPIN_DEBUG
-    { int sp = 0; cudaMemcpy(&sp, ctx->d_rr_ctl.as<int>() + 8, 4, cudaMemcpyDeviceToHost); S.n_sub_batches = sp; }
-#endif
     ctx->ran = true;
     return NPORE_OK;
 }

@@ -17,6 +17,7 @@
 #define NP_REC_IE 0x0800u
 #define NP_REC_DE 0x1000u
 #define NP_PAD 96          // zero records after every colrec/rowrec slice (band prefetch runs ahead)
+#define NP_TABQ 128        // entries per row of the re-laid score tables (run/n clamped to NP_TABQ-1; forward.cuh)
 
 enum { T_MAT = 0, T_INS = 1, T_LEN = 2, T_DEL = 3, T_SHR = 4 };   // aln.pyx:411-416
 
@@ -49,7 +50,7 @@ struct ChunkDesc {
 
 // Scratch placement of one chunk inside the current sub-batch (assigned on the host from size upper bounds).
 struct ChunkSlot {
-    int64_t col_off;    // first colrec entry (8 B each); the raw/nf/lf scratch of the ref slice uses the same offsets
+    int64_t col_off;    // first colrec entry (32 B each); the raw scratch of the ref slice uses the same offsets
     int64_t row_off;    // first rowrec entry (4 B each); likewise for the read slice
     int64_t tb_off;     // first traceback row; row stride = 32*TBS uint16
     int32_t col_cap, row_cap;   // entries reserved (>= slice length + NP_PAD)
@@ -65,7 +66,7 @@ struct ChunkOut {
 struct AlignParams {
     int r, W, max_n, max_l, max_b_rows;
     int np_dim, np_clamp;       // table side (101) and the index clamp max_l-1 (aln.pyx:269-272 as called at :615)
-    int np_rows;                // np_n * np_dim: index of the all-INF guard row of the re-laid table
+    int np_rows;                // max_n * (max_l+1): rows of each re-laid table; row np_rows is all +INF ("no candidate")
     float gap_open, gap_ext;
 };
 
