@@ -275,28 +275,193 @@ def select_reads(bam, regions=None, max_reads=0):
 _PIPES = {}
 
 
-def _pipeline(sub, npt, n_inflight):
-    """Cached PipelinedRealigner for the current cfg / tables (same idea as aln._engine)."""
+def _pipeline(sub, npt, n_inflight, device=None):
+    """Cached PipelinedRealigner per (tables, cfg, device) (same idea as aln._engine)."""
     from .engine import PipelinedRealigner
-    key = (np.asarray(sub, np.float32).tobytes(), hash(np.asarray(npt, np.float32).tobytes()), int(cfg.args.max_n), int(cfg.args.max_l),
-           int(getattr(cfg.args, "device", 0) or 0), n_inflight)
-    p = _PIPES.get(key)
+    dev = int(getattr(cfg.args, "device", 0) or 0) if device is None else int(device)
+    key = (np.asarray(sub, np.float32).tobytes(), hash(np.asarray(npt, np.float32).tobytes()), int(cfg.args.max_n), int(cfg.args.max_l), n_inflight)
+    for old in [k for k in _PIPES if k[0] != key]:          # tables / cfg changed: drop every cached pipeline
+        _PIPES.pop(old).close()
+    p = _PIPES.get((key, dev))
     if p is None:
-        for old in list(_PIPES):
-            _PIPES.pop(old).close()
-        p = _PIPES[key] = PipelinedRealigner(sub, npt, n_inflight=n_inflight, max_n=int(cfg.args.max_n), max_l=int(cfg.args.max_l),
-                                             device=int(getattr(cfg.args, "device", 0) or 0))
+        p = _PIPES[(key, dev)] = PipelinedRealigner(sub, npt, n_inflight=n_inflight, max_n=int(cfg.args.max_n), max_l=int(cfg.args.max_l), device=dev)
     return p
 
 
+def _read_loads(bam, sel, max_b_rows=20000, r=30):
+    """Cell updates per selected record: (Lref + Lseq + n_chunks) * (2r+1), from the record columns alone."""
+    ops = (bam.end[sel] - bam.pos[sel]).astype(np.int64) + bam.aln_len[sel]
+    return (ops + -(-ops // (max_b_rows - 1))) * (2 * r + 1)
+
+
+def _realign_segments(bam, segments, fa, codes, codes_lock, pipe, fh, tm, n_threads, max_batch_ops, n_inflight):
+    """The three-stage pipeline over an explicit list of (contig, record indices) segments: gather batch k+1 while batch k is
+    on the GPU and batch k-1 is formatted and written to `fh` -- records in segment order.  Returns the records written."""
+    import queue
+    import threading
+    import time
+    from .aln import _report
+    from .cig import bases_to_int
+    from .engine import NPORE_OUT_NO_EXPANDED, NPORE_OUT_RLE, NPORE_OUT_STANDARDIZE, PackedBatch
+    flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED
+    pending = queue.Queue(maxsize=n_inflight + 1)
+    state = {"written": 0, "error": None}
+
+    def retire_loop():
+        while True:
+            item = pending.get()
+            if item is None:
+                return
+            if state["error"] is not None:
+                continue
+            try:
+                fut, cols, g, n = item
+                t1 = time.perf_counter()
+                res, _ = fut.result()
+                t2 = time.perf_counter()
+                _report(res.status[:n], "realign_read")
+                blob = format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols)
+                t3 = time.perf_counter()
+                fh.write(memoryview(blob))
+                tm["gpu_wait"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += time.perf_counter() - t3
+                state["written"] += n
+            except Exception as e:                    # noqa: BLE001
+                state["error"] = e
+
+    retire = threading.Thread(target=retire_loop, daemon=True)
+    retire.start()
+    try:
+        for ctg, sel in segments:
+            with codes_lock:
+                if ctg not in codes:
+                    codes[ctg] = bases_to_int(fa[ctg].upper())
+                cc = codes[ctg]
+            ops = np.cumsum((bam.end[sel] - bam.pos[sel]).astype(np.int64) + bam.aln_len[sel])
+            cut = 0
+            while cut < len(sel) and state["error"] is None:
+                stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
+                part = sel[cut:stop]
+                t1 = time.perf_counter()
+                g = bam.gather(part, n_threads)
+                lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
+                packed = PackedBatch.from_flat_shared(cc[lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
+                                                      g["seq_codes"][:int(g["seq_off"][-1])], bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
+                item = (pipe.submit(packed, flags), take_columns(bam, part), g, len(part))
+                tm["gather"] += time.perf_counter() - t1
+                pending.put(item)
+                cut = stop
+    finally:
+        pending.put(None)
+        retire.join()
+    if state["error"] is not None:
+        raise state["error"]
+    return state["written"]
+
+
+def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, max_reads=0, argv=None, max_batch_ops=64_000_000,
+                        n_threads=0, timings=None, n_inflight=2):
+    """realign.py:75-115 on several GPUs of one host: the coordinate-sorted reads are cut into len(devices)
+    contiguous genomic regions of equal cell-update load (the reference's own unit of distribution is the region,
+    util.py:44-93 / bam.pyx:27-28); every region is an independent ingest -> GPU -> SAM-text pipeline on its own device (no
+    data-path collective); the host gathers the per-region SAM bodies in region order into ONE file, byte-identical to the
+    single-GPU output.  `devices` may name a device more than once (several pipelines on one GPU).  timings: per phase, summed
+    over the shards, plus 'shards': [{device, reads, cell_updates, seconds}] and 'concat' seconds."""
+    import shutil
+    import threading
+    import time
+    from .bam import _tables
+    tm = timings if timings is not None else {}
+    for k in ("open", "gather", "gpu_wait", "format", "write", "concat"):
+        tm.setdefault(k, 0.0)
+    t0 = time.perf_counter()
+    if out_prefix is not None:
+        cfg.args.out_prefix = out_prefix
+    if not os.path.exists(bam_fn):
+        print(f"\nERROR: BAM file '{bam_fn}' not found.")
+        sys.exit(1)
+    fa = read_fasta(fasta) if isinstance(fasta, str) else fasta
+    bam = NativeBam(bam_fn, n_threads, window_bytes=0)             # region cuts need every record's span
+    out = f"{cfg.args.out_prefix}.sam"
+    create_header(out, bam.refs, argv)
+    sub, npt = _tables()
+    G = len(devices)
+    segs = list(select_reads(bam, regions, max_reads))
+    loads = [_read_loads(bam, sel) for _, sel in segs]
+    total = float(sum(int(x.sum()) for x in loads))
+    # contiguous cuts of the (contig, start)-ordered read list at equal cumulative load
+    shard_segs = [[] for _ in range(G)]
+    shard_load = [0] * G
+    done = 0.0
+    for (ctg, sel), ld in zip(segs, loads):
+        cs = done + np.cumsum(ld, dtype=np.float64)
+        owner = np.minimum((cs - ld / 2.0) * G / max(total, 1.0), G - 1).astype(np.int64)       # by the read's load midpoint
+        for gidx in np.unique(owner):
+            m = owner == gidx
+            shard_segs[int(gidx)].append((ctg, sel[m]))
+            shard_load[int(gidx)] += int(ld[m].sum())
+        done = float(cs[-1]) if len(cs) else done
+    tm["open"] += time.perf_counter() - t0
+    codes, codes_lock = {}, threading.Lock()
+    parts = [out if g == 0 else f"{cfg.args.out_prefix}.part{g}.sam" for g in range(G)]
+    results = [None] * G
+    thread_tm = [{k: 0.0 for k in ("gather", "gpu_wait", "format", "write")} for _ in range(G)]
+
+    def shard_main(g):
+        t1 = time.perf_counter()
+        try:
+            pipe = _pipeline(sub, npt, n_inflight, devices[g])
+            with open(parts[g], "ab" if g == 0 else "wb") as fh:
+                n = _realign_segments(bam, shard_segs[g], fa, codes, codes_lock, pipe, fh, thread_tm[g], max(1, (n_threads or os.cpu_count() or 1) // G),
+                                      max_batch_ops, n_inflight)
+            results[g] = (n, time.perf_counter() - t1, None)
+        except Exception as e:      # noqa: BLE001
+            results[g] = (0, time.perf_counter() - t1, e)
+
+    with _PIPE_LOCK:                # contexts of different devices are created one after the other
+        for g in range(G):
+            _pipeline(sub, npt, n_inflight, devices[g])
+    threads = [threading.Thread(target=shard_main, args=(g,)) for g in range(G)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for n, _, err in results:
+        if err is not None:
+            raise err
+    t2 = time.perf_counter()
+    with open(out, "ab") as fh:                                     # host gather: region order = coordinate order
+        for g in range(1, G):
+            with open(parts[g], "rb") as src:
+                shutil.copyfileobj(src, fh, 16 << 20)
+            os.remove(parts[g])
+    tm["concat"] += time.perf_counter() - t2
+    for k in ("gather", "gpu_wait", "format", "write"):
+        tm[k] += sum(x[k] for x in thread_tm)
+    tm["shards"] = [{"device": int(devices[g]), "reads": int(results[g][0]), "cell_updates": int(shard_load[g]), "seconds": round(results[g][1], 4)}
+                    for g in range(G)]
+    written = sum(n for n, _, _ in results)
+    with cfg.counter.get_lock():
+        cfg.counter.value += written
+    bam.close()
+    return written
+
+
+import threading as _threading  # noqa: E402
+_PIPE_LOCK = _threading.Lock()
+
+
 def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=None, max_batch_ops=64_000_000, n_threads=0,
-                timings=None, window_bytes=64 << 20, n_inflight=2):
+                timings=None, window_bytes=64 << 20, n_inflight=2, devices=None):
     """realign.py:75-115 without pysam / Pool: header, ingest, GPU realignment, records appended in input order
     (= coordinate order for a sorted BAM, which is what the header claims).  Returns the number of records written.
     Flat arrays all the way, as a pipeline: the reader streams the file in windows of ~window_bytes of inflated records
     (native, multi-threaded) and gathers batch k+1 while batch k is on the GPU (n_inflight contexts) and a third thread
     formats (native) and writes batch k-1.  One shared reference slice is uploaded per batch.
-    timings: optional dict that receives host seconds per phase (open, gather, gpu_wait, format, write)."""
+    timings: optional dict that receives host seconds per phase (open, gather, gpu_wait, format, write).
+    devices: CUDA device indices; more than one -> realign_bam_sharded (one region-shard pipeline per device, ordered gather)."""
+    if devices is not None and len(devices) > 1:
+        return realign_bam_sharded(bam_fn, fasta, list(devices), out_prefix=out_prefix, regions=regions, max_reads=max_reads, argv=argv,
+                                   max_batch_ops=max_batch_ops, n_threads=n_threads, timings=timings, n_inflight=n_inflight)
     import queue
     import threading
     import time
@@ -319,7 +484,7 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
     streaming = bam.window_bytes > 0
     create_header(f"{cfg.args.out_prefix}.sam", bam.refs, argv)
     sub, npt = _tables()
-    pipe = _pipeline(sub, npt, n_inflight)
+    pipe = _pipeline(sub, npt, n_inflight, devices[0] if devices else None)
     flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED
     codes = {}
     tm["open"] += time.perf_counter() - t0

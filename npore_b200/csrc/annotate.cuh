@@ -27,7 +27,7 @@
 //           [1] k-mer contains N  [2:4] base ref[j-1]  [8:19] 2-bit k-mer ref[j..j+5]
 //     LEN = descriptor of the single LEN-eligible period at j: [0:2] n  [3:12] table row  [20:25] one-hot period mask
 //           aligned with rowrec's "tract present" bits (bit 19+n)
-//   rowrec[i] (uint32): [4] k-mer contains N  [5:7] base seq[i-1]  [8:19] 2-bit k-mer seq[i-6..i-1] (the LEN unit
+//   rowrec[i] (uint32): [1] k-mer contains N  [5:7] base seq[i-1]  [8:19] 2-bit k-mer seq[i-6..i-1] (the LEN unit
 //                       seq[i-n..i) is its last n codes)
 //                       [20:25] tract present at i-n (bit 19+n)  [26:31] tract start at i-n (bit 25+n, L_IDX==0)
 #pragma once
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                 const uint32_t base = (i >= 1 && i - 1 < len) ? s[i - 1] : 0u;
                 uint32_t hasN = 0;
                 const uint32_t km = kmer2_of(s, len, i - 6, hasN);      // the 6-mer ending at seq[i-1]
-                v |= hasN << 4 | (base & 7u) << 5 | km << 8;
+                v |= hasN << 1 | (base & 7u) << 5 | km << 8;
             }
             out[i] = v;
         }

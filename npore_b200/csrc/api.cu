@@ -12,6 +12,7 @@
 //   download : per-item op strings, run-length words, chunk scores, status -> host
 // There is no CPU fallback: every entry point fails with NPORE_ERR_NO_DEVICE / NPORE_ERR_CUDA without a GPU.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,15 +32,23 @@ namespace {
 
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
+    // grow-only; contents are NOT preserved.  The new block is allocated before the old one is released, so a failed growth
+    // leaves the buffer usable at its old size; only if both do not fit is the old block given up first.
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        void *q = nullptr;
         size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); want = bytes; }
-        if (e == cudaSuccess) cap = want;
-        return e;
+        cudaError_t e = cudaMalloc(&q, want);
+        if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&q, want); }
+        if (e != cudaSuccess && p) {
+            cudaGetLastError();
+            cudaFree(p); p = nullptr; cap = 0;
+            e = cudaMalloc(&q, want);
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); return e; }
+        if (p) cudaFree(p);
+        p = q; cap = want;
+        return cudaSuccess;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
@@ -59,6 +68,8 @@ struct HostBuf {      // pinned staging owned by the library (download path)
 };
 
 struct SubBatch { int first, count; };
+
+std::atomic<int> g_ctx_on_device[64];      // live contexts per device: they share the scratch budget (PipelinedRealigner)
 
 }  // namespace
 
@@ -86,7 +97,7 @@ struct npore_ctx {
     std::vector<ChunkSlot> slots;
     std::vector<SubBatch> subs;
     int64_t n_chunks = 0, total_ops = 0, total_rle = 0, total_words = 0;
-    bool uploaded = false, ran = false;
+    bool uploaded = false, ran = false, counted = false, budget_fixed = false;
     uint32_t run_flags = 0;
     npore_stats stats{};
     cudaEvent_t ev[8]{};
@@ -208,7 +219,7 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     // score tables re-laid per (period n, tract length L) so that a candidate is one load (forward.cuh): row (n-1)*(max_l+1)+L,
     //   tabS[row][q] = np_score(n, L, -(q+1))   (SHR after q = trunc(run/n) units already removed)
     //   tabL[row][q] = np_score(n, L, +(q+1))   (LEN likewise)
-    // with np_score exactly as the reference CALLS it (aln.pyx:257-274 with max_l in the max_n slot, :615): 100.0 if
+    // (q up to the saturated run NP_RUN_SAT < NP_TABQ, so the kernel never clamps it) with np_score exactly as the reference CALLS it (aln.pyx:257-274 with max_l in the max_n slot, :615): 100.0 if
     // L + indel < 0, else np_scores[n-1][min(L, max_l-1)][min(L + indel, max_l-1)].  Row `rows` is all +INF ("no candidate").
     {
         const int rows = max_n * (max_l + 1), clampv = max_l - 1;
@@ -220,7 +231,7 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
                         const int call = sgn ? L + q + 1 : L - q - 1;
                         float v = 100.0f;
                         if (call >= 0) v = np_scores[((size_t)(n - 1) * np_dim + std::min(L, clampv)) * np_dim + std::min(call, clampv)];
-                        tab[((size_t)sgn * (rows + 1) + (size_t)(n - 1) * (max_l + 1) + L) * NP_TABQ + q] = v;
+                        tab[((size_t)sgn * NP_TABQ + q) * (rows + 1) + (size_t)(n - 1) * (max_l + 1) + L] = v;      // q-major: the hot q = 0, 1, 2 of ALL rows share a few cache lines
                     }
         if (ctx->d_np.ensure(tab.size() * sizeof(float)) != cudaSuccess) return bail(NPORE_ERR_OOM);
         if (cudaMemcpy(ctx->d_np.p, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) return bail(NPORE_ERR_CUDA);
@@ -230,8 +241,10 @@ int npore_ctx_create(npore_ctx **out, int device, const float *sub_scores, const
     size_t fr = 0, tot = 0;
     cudaMemGetInfo(&fr, &tot);
     if (cudaGetLastError() != cudaSuccess) return bail(NPORE_ERR_CUDA);
-    ctx->scratch_budget = (size_t)((double)fr * 0.55);
-    if (const char *s = getenv("NPORE_SCRATCH_MB")) ctx->scratch_budget = (size_t)atoll(s) << 20;
+    ctx->scratch_budget = (size_t)((double)fr * 0.55);          // divided by the device's live contexts at run time
+    if (device < 64) g_ctx_on_device[device]++;
+    ctx->counted = true;
+    if (const char *s = getenv("NPORE_SCRATCH_MB")) { ctx->scratch_budget = (size_t)atoll(s) << 20; ctx->budget_fixed = true; }
     if (const char *s = getenv("NPORE_RR_SLICE")) ctx->rr_slice = std::max(8, atoi(s));
     *out = ctx;
     return NPORE_OK;
@@ -241,6 +254,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->counted && ctx->device < 64) g_ctx_on_device[ctx->device]--;
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
                       &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,

@@ -17,7 +17,7 @@
 #define NP_REC_IE 0x0800u
 #define NP_REC_DE 0x1000u
 #define NP_PAD 96          // zero records after every colrec/rowrec slice (band prefetch runs ahead)
-#define NP_TABQ 128        // entries per row of the re-laid score tables (run/n clamped to NP_TABQ-1; forward.cuh)
+#define NP_TABQ 2048       // q = trunc(run/n) entries of the re-laid score tables (run saturates at NP_RUN_SAT < NP_TABQ; forward.cuh)
 
 enum { T_MAT = 0, T_INS = 1, T_LEN = 2, T_DEL = 3, T_SHR = 4 };   // aln.pyx:411-416
 

@@ -55,7 +55,7 @@ struct ForwardArgs {
     const uint2 *relaid;
     const uint32_t *rowrec;
     uint16_t *tb;
-    const float *tab;             // tabS rows [np_rows+1][NP_TABQ], then tabL likewise
+    const float *tab;             // tabS [NP_TABQ][np_rows+1] (q-major), then tabL likewise
     const float *sub_tab;         // [5][5]  indexed [seq_base][ref_base]
     ChunkOut *out;                // indexed by chunk id
     // round-robin time slicing: run queue + per-chunk saved state
@@ -119,19 +119,22 @@ __device__ __forceinline__ float bitsel_f(uint32_t m, float x, float y) { return
 //   B ceil(65536 / n)        C 0 (start) or 0xffff0000 (continue: SHR.RUN << 16 of the source)
 // An empty descriptor addresses the +INF table row.  `ok` is the checked variant's source test (always true when lean).
 template <int NC>
-__device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uint32_t dsh, uint32_t wbase, const float *__restrict__ tabS,
+__device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uint32_t dsh, uint32_t wbase, const float *__restrict__ tabS, uint32_t trows,
                                          bool ok, float &Sv, float &Sb, uint32_t &Sr)
 {
     const uint32_t ad = (((A >> 16) + dsh) & (uint32_t)(NC * 128 - 8)) | wbase;
     float base; uint32_t w;
     lds_pair(ad, base, w);
     const uint32_t xs = w & C;                                        // SHR.RUN << 16 of the source, 0 at a tract start
-    const uint32_t q = min(__umulhi(xs, B), (uint32_t)(NP_TABQ - 1)); // trunc(run / n), clamped
-    const float cand = base + __ldg(tabS + ((A & 0xffffu) * (uint32_t)NP_TABQ + q));
+    const uint32_t q = __umulhi(xs, B);                               // trunc(run / n) <= NP_RUN_SAT < NP_TABQ
+    const float cand = base + __ldg(tabS + (q * trows + (A & 0xffffu)));
     const bool better = ok && cand < Sv;
     const uint32_t nr = __viaddmin_u32(xs, A & 0x70000u, FWD_SAT16);
     Sv = better ? cand : Sv; Sb = better ? base : Sb; Sr = better ? nr : Sr;
 }
+
+__device__ __forceinline__ float fmin3(float a, float b, float c)
+{ float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
 template <int CPL>
 __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const ForwardArgs a)
@@ -165,9 +168,9 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
 
     const int r = a.P.r;
     const float gopen = a.P.gap_open, gext = a.P.gap_ext;
-    const uint32_t nmask = ((1u << a.P.max_n) - 1u) << 20;      // rowrec "present" bits live at [20:25]
     const float *__restrict__ tabS = a.tab;
     const float *__restrict__ tabL = a.tab + (size_t)(a.P.np_rows + 1) * NP_TABQ;
+    const uint32_t trows = (uint32_t)a.P.np_rows + 1u;          // row stride of the q-major score tables
     const uint32_t empty_A = (uint32_t)a.P.np_rows;             // annotate.cuh: "no candidate" -> the +INF table row
     const int src_lane = (lane + 31) & 31;
     const int spare = NC - (2 * r + 1);
@@ -310,18 +313,18 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
             }
             const float edgev = infd + 100.f;
 
-            uint32_t inm[CPL];
+            bool in[CPL];
             int bc[CPL];                                  // numeric b_col (checked variant only)
             if (STEADY) {
 #pragma unroll
-                for (int k = 0; k < CPL; k++) inm[k] = es[k] <= in_lim ? 0xffffffffu : 0u;
+                for (int k = 0; k < CPL; k++) in[k] = es[k] <= in_lim;
             } else {      // interior-cell bounds on b_col for this anti-diagonal (aln.pyx:497-507)
                 int lo = max(1, max(Id + r - imax, r - Dd)), hi = min(2 * r - 1, min(Id + r, jmax + r - Dd));
                 if (hi < lo) { lo = 1; hi = 0; }
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
                     bc[k] = (int)(((es[k] >> SH) + 1u) & (uint32_t)(NC - 1));
-                    inm[k] = ((unsigned)(bc[k] - lo) <= (unsigned)(hi - lo) && hi >= lo) ? 0xffffffffu : 0u;
+                    in[k] = (unsigned)(bc[k] - lo) <= (unsigned)(hi - lo) && hi >= lo;
                 }
             }
             // #I among the last n ops, n = 1..6, 4 bits each at nibble n (checked variant: source tests)
@@ -337,24 +340,24 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 Sv[k] = infd; Lv[k] = infd; Sb[k] = __uint_as_float(FWD_INF_BITS); Lb[k] = __uint_as_float(FWD_INF_BITS); Sr[k] = 0u; Lr[k] = 0u;
-                const uint32_t lw = rw[k] & cb[k].w & nmask & inm[k];      // one-hot LEN period vs "tract present" bits
-                pl[k] = lw != 0u;
-                pg[k] = (cb[k].z & inm[k] & 1u) != 0u;
-                any1 |= ca[k].w ^ empty_A; anyl |= lw; anyg |= cb[k].z & inm[k];
+                const uint32_t lw = rw[k] & cb[k].w & 0x03f00000u;          // one-hot LEN period vs the row's "tract present" bits
+                pl[k] = in[k] && lw != 0u;
+                pg[k] = in[k] && (cb[k].z & 1u) != 0u;
+                any1 |= ca[k].w ^ empty_A; anyl |= lw; anyg |= cb[k].z;          // (votes on the unmasked words: slightly conservative)
             }
             // ---- SHR gather: descriptor 0 (largest period), then descriptor 1 if any lane has one
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 bool ok = true;
-                if (!STEADY) { const uint32_t n = (ca[k].x >> 16) & 7u; ok = inm[k] && bc[k] > (int)((sip >> (4 * n)) & 7u); }
-                shr_eval<NC>(ca[k].x, ca[k].y, ca[k].z, dsh, wbase, tabS, ok, Sv[k], Sb[k], Sr[k]);
+                if (!STEADY) { const uint32_t n = (ca[k].x >> 16) & 7u; ok = in[k] && bc[k] > (int)((sip >> (4 * n)) & 7u); }
+                shr_eval<NC>(ca[k].x, ca[k].y, ca[k].z, dsh, wbase, tabS, trows, ok, Sv[k], Sb[k], Sr[k]);
             }
             if (__any_sync(NP_FULL, any1 != 0u)) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
                     bool ok = true;
-                    if (!STEADY) { const uint32_t n = (ca[k].w >> 16) & 7u; ok = inm[k] && bc[k] > (int)((sip >> (4 * n)) & 7u); }
-                    shr_eval<NC>(ca[k].w, cb[k].x, cb[k].y, dsh, wbase, tabS, ok, Sv[k], Sb[k], Sr[k]);
+                    if (!STEADY) { const uint32_t n = (ca[k].w >> 16) & 7u; ok = in[k] && bc[k] > (int)((sip >> (4 * n)) & 7u); }
+                    shr_eval<NC>(ca[k].w, cb[k].x, cb[k].y, dsh, wbase, tabS, trows, ok, Sv[k], Sb[k], Sr[k]);
                 }
             }
             // ---- LEN gather (aln.pyx:602-633): single eligible period, 2-bit k-mer unit compare in registers
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
                 for (int k = 0; k < CPL; k++) {
                     if (pl[k]) {
                         const uint32_t D = cb[k].w;
-                        if ((cb[k].z | (rw[k] >> 3)) & 2u) {
+                        if ((cb[k].z | rw[k]) & 2u) {
                             pg[k] = true; anyg |= 1u;              // an N inside a k-mer: byte-wise compare on the generic path
                         } else {
                             const uint32_t n = D & 7u;
@@ -376,8 +379,8 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
                             const uint32_t ad = ((dsh - n * ROWB + mypos[k]) & (RING_BYTES - 16u)) | wbase;
                             const float base = lds_f(ad + (start ? 0u : 4u));                       // MAT.VAL or the carried LEN run-start value
                             const uint32_t run0 = start ? 0u : (lds_u_off<12>(ad) & 0xffffu);
-                            const uint32_t q = min(__umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u)), (uint32_t)(NP_TABQ - 1));
-                            const float cand = base + __ldg(tabL + (((D >> 3) & 0x3ffu) * (uint32_t)NP_TABQ + q));
+                            const uint32_t q = __umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u));
+                            const float cand = base + __ldg(tabL + (q * trows + ((D >> 3) & 0x3ffu)));
                             if (ok && cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + n, (uint32_t)NP_RUN_SAT) << 16; Lb[k] = base; }
                         }
                     }
@@ -401,10 +404,10 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
                                 const uint32_t sslot = (uint32_t)(j - n) & (uint32_t)(NC - 1);
                                 const uint32_t off = (uint32_t)((-n) & (NP_RING - 1)) * ROWB + ((sslot % CPL) * 32u + sslot / CPL) * 16u + ((byte & 0x80u) ? 0u : 8u);
                                 const uint32_t A = ((off | (uint32_t)n) << 16) | (uint32_t)((n - 1) * (a.P.max_l + 1) + (int)L);
-                                shr_eval<NC>(A, lds_u_off<0>(m16base + n * 4u), (byte & 0x80u) ? 0u : 0xffff0000u, dsh, wbase, tabS, true, Sv[k], Sb[k], Sr[k]);
+                                shr_eval<NC>(A, lds_u_off<0>(m16base + n * 4u), (byte & 0x80u) ? 0u : 0xffff0000u, dsh, wbase, tabS, trows, true, Sv[k], Sb[k], Sr[k]);
                             }
                         }
-                        uint32_t lm = (rb.y >> 22) & ((rw[k] & nmask) >> 20) & 0x3fu;   // LEN, every eligible period
+                        uint32_t lm = (rb.y >> 22) & (rw[k] >> 20) & 0x3fu;   // LEN, every eligible period
                         while (lm) {
                             const int n = 32 - __clz(lm);
                             lm &= ~(1u << (n - 1));
@@ -419,8 +422,8 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
                             const uint32_t ad = ((dsh - (uint32_t)n * ROWB + mypos[k]) & (RING_BYTES - 16u)) | wbase;
                             const float base = lds_f(ad + (start ? 0u : 4u));
                             const uint32_t run0 = start ? 0u : (lds_u_off<12>(ad) & 0xffffu);
-                            const uint32_t q = min(__umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u)), (uint32_t)(NP_TABQ - 1));
-                            const float cand = base + __ldg(tabL + ((uint32_t)((n - 1) * (a.P.max_l + 1) + L) * (uint32_t)NP_TABQ + q));
+                            const uint32_t q = __umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u));
+                            const float cand = base + __ldg(tabL + (q * trows + (uint32_t)((n - 1) * (a.P.max_l + 1) + L)));
                             if (cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + (uint32_t)n, (uint32_t)NP_RUN_SAT) << 16; Lb[k] = base; }
                         }
                     }
@@ -430,54 +433,53 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
             // ---- INS / DEL / MAT (aln.pyx:525-592); records are assembled in the upper half word
             uint32_t pk[CPL];
             float Mv[CPL], Iv[CPL], Dv[CPL];
+            const uint32_t rowad = (dsh & (RING_BYTES - 1u)) | wbase;
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 // INS from top = own previous value; DEL from left.  Only the "extended" bits are kept (see common.cuh)
                 const float iv1 = Mv1[k] + gopen, iv2 = Iv1[k] + gext;
                 bool iext = iv2 < iv1;                                               // aln.pyx:536
-                Iv[k] = iext ? iv2 : iv1;
+                Iv[k] = fminf(iv1, iv2);
                 const float dv1 = lMv[k] + gopen, dv2 = lDv[k] + gext;
                 bool dext = dv2 < dv1;                                               // aln.pyx:558
-                Dv[k] = dext ? dv2 : dv1;
-                uint32_t p = __viaddmin_u32(dgr[k], 0x10000u, FWD_SAT16);            // typ MAT = 0
-                float best = dgv[k] + lds_f(subbase + (rw[k] & 0xe0u) + (cb[k].z & 0x1cu));
+                Dv[k] = fminf(dv1, dv2);
+                uint32_t pm = __viaddmin_u32(dgr[k], 0x10000u, FWD_SAT16);           // typ MAT = 0
+                float dg = dgv[k] + lds_f(subbase + ((rw[k] | cb[k].z) & 0xfcu));    // sub_scores[seq[i-1]][ref[j-1]] (aln.pyx:575)
                 if (!STEADY) {
                     const int i = Id + r - bc[k], j = Dd - r + bc[k];
                     if (i <= 1) iext = false;                                        // aln.pyx:537-538 (run restarts), :525-528
                     if (j <= 1) dext = false;                                        // aln.pyx:559-560, :547-550
                     if (i == 0) Iv[k] = (float)(100 * (j + 1));
                     if (j == 0) Dv[k] = (float)(100 * (i + 1));
-                    if (!(i > 0 && j > 0)) { best = Dv[k] + 100.f; p = 0u; }
+                    if (!(i > 0 && j > 0)) { dg = Dv[k] + 100.f; pm = 0u; }
                 }
-                if (Iv[k] < best) { best = Iv[k]; p = (uint32_t)T_INS << 29; }
-                if (Lv[k] < best) { best = Lv[k]; p = ((uint32_t)T_LEN << 29) | Lr[k]; }
-                if (Dv[k] < best) { best = Dv[k]; p = (uint32_t)T_DEL << 29; }
-                if (Sv[k] < best) { best = Sv[k]; p = ((uint32_t)T_SHR << 29) | Sr[k]; }
-                p &= inm[k];
-                Mr1[k] = p < (1u << 29) ? p : 0u;                                   // match run of this cell (0 unless TYP == MAT)
-                if (iext) p |= inm[k] & (NP_REC_IE << 16);
-                if (dext) p |= inm[k] & (NP_REC_DE << 16);
+                // MAT = the first minimum in the order diag, INS, LEN, DEL, SHR (strict '<' chain of aln.pyx:585-592)
+                const float best = fmin3(fmin3(dg, Iv[k], Lv[k]), Dv[k], Sv[k]);
+                uint32_t p = ((uint32_t)T_SHR << 29) | Sr[k];
+                if (Dv[k] == best) p = (uint32_t)T_DEL << 29;
+                if (Lv[k] == best) p = ((uint32_t)T_LEN << 29) | Lr[k];
+                if (Iv[k] == best) p = (uint32_t)T_INS << 29;
+                if (dg == best) p = pm;
+                if (!in[k]) p = 0u;
+                Mr1[k] = dg == best && in[k] ? pm : 0u;                              // match run of this cell (0 unless TYP == MAT)
+                if (iext && in[k]) p |= NP_REC_IE << 16;
+                if (dext && in[k]) p |= NP_REC_DE << 16;
                 pk[k] = p;
+                // history ring: every slot writes; +INF unless the cell is interior
+                sts_slot(rowad + mypos[k], in[k] ? best : __uint_as_float(FWD_INF_BITS), Lb[k], in[k] ? Sb[k] : __uint_as_float(FWD_INF_BITS),
+                         __byte_perm(Lr[k], Sr[k], 0x7632));
                 // EDGE (b_col 0 / 2r): every state INF*(b_row+1), TYP MAT, RUN 0 (aln.pyx:502-507).  Cells outside the chunk
                 // (aln.pyx:497-499) are never read by interior cells; they get the same harmless value.
-                Mv[k] = bitsel_f(inm[k], best, edgev);
-                Iv[k] = bitsel_f(inm[k], Iv[k], edgev);
-                Dv[k] = bitsel_f(inm[k], Dv[k], edgev);
+                Mv[k] = in[k] ? best : edgev;
+                Iv[k] = in[k] ? Iv[k] : edgev;
+                Dv[k] = in[k] ? Dv[k] : edgev;
             }
-
-            // ---- history ring (every slot: +INF unless interior) + traceback row (slot order)
-            {
-                const uint32_t rowad = (dsh & (RING_BYTES - 1u)) | wbase;
+            // ---- traceback row (slot order), streamed once, read once by the traceback
+            if (CPL == 1) __stcs(reinterpret_cast<unsigned short *>(rowp), (unsigned short)(pk[0] >> 16));
+            else {
 #pragma unroll
-                for (int k = 0; k < CPL; k++)
-                    sts_slot(rowad + mypos[k], bitsel_f(inm[k], Mv[k], __uint_as_float(FWD_INF_BITS)), Lb[k],
-                             bitsel_f(inm[k], Sb[k], __uint_as_float(FWD_INF_BITS)), __byte_perm(Lr[k], Sr[k], 0x7632));
-                if (CPL == 1) __stcs(reinterpret_cast<unsigned short *>(rowp), (unsigned short)(pk[0] >> 16));
-                else {
-#pragma unroll
-                    for (int k = 0; k < CPL; k += 2)      // streamed once, read once by the traceback
-                        __stcs(reinterpret_cast<unsigned int *>(rowp) + (k >> 1), __byte_perm(pk[k], pk[k + 1 < CPL ? k + 1 : k], 0x7632));
-                }
+                for (int k = 0; k < CPL; k += 2)
+                    __stcs(reinterpret_cast<unsigned int *>(rowp) + (k >> 1), __byte_perm(pk[k], pk[k + 1 < CPL ? k + 1 : k], 0x7632));
             }
             __syncwarp();
 #pragma unroll
