@@ -60,7 +60,16 @@ def align_batch(refs, seqs, cigars, sub_scores, np_scores, indel_start=5, indel_
 
 def align(full_ref, full_seq, cigar, sub_scores, np_scores, indel_start=5, indel_extend=1, max_b_rows=20000, r=30,
           verbose=0):
-    """aln.pyx:379-382, same positional / keyword signature and return value (expanded CIGAR over '=XID')."""
+    """aln.pyx:379-382, same positional / keyword signature and return value (expanded CIGAR over '=XID').
+    verbose: the reference prints its five (VAL, TYP, RUN) matrices (aln.pyx:744-785); they never exist here (2 bytes per cell
+    reach memory), so verbose prints the per-chunk scores and the alignment instead."""
+    if verbose:
+        outs, scores = align_batch([np.asarray(full_ref, dtype=np.uint8)], [np.asarray(full_seq, dtype=np.uint8)], [cigar],
+                                   sub_scores, np_scores, indel_start, indel_extend, max_b_rows, r, return_scores=True)
+        print(f"align(verbose): {len(scores[0])} chunk(s), chunk scores {[float(x) for x in scores[0]]}; the DP matrices are not "
+              "materialised on the GPU path (only the packed MAT record per cell)")
+        print(f"align(verbose): CIGAR {outs[0]}")
+        return outs[0]
     return align_batch([np.asarray(full_ref, dtype=np.uint8)], [np.asarray(full_seq, dtype=np.uint8)], [cigar],
                        sub_scores, np_scores, indel_start, indel_extend, max_b_rows, r)[0]
 

@@ -65,6 +65,9 @@ def realign_haps(hap_data, max_batch_ops=300_000_000):
     sub, npt = _tables()
     eng = _engine(sub, npt, 5, 1, 20000, 30)
     out = []
+    hap_data = list(hap_data)
+    from .engine import check_item_sizes
+    check_item_sizes([len(h[3]) for h in hap_data], [len(h[2]) for h in hap_data], what="haplotype")     # per item, before any batch runs
     for batch in iter_batches(hap_data, lambda h: len(h[2]) + len(h[3]), max_batch_ops):
         packed = PackedBatch.from_strings([h[3] for h in batch], [h[2] for h in batch], [h[4] for h in batch])
         res = eng.align_packed(packed, NPORE_OUT_STANDARDIZE, eng.new_result(packed, NPORE_OUT_STANDARDIZE, pinned=False))

@@ -144,7 +144,8 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
     cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device);
     const size_t start = (size_t)reserved + fattr.sharedSizeBytes;
     const size_t slack = (RING - start % RING) % RING;
-    const size_t smem = (size_t)WARPS * RING + slack;
+    // + the per-warp column-record FIFOs (1 KB each): inside the slack when it is large enough, else behind the rings
+    const size_t smem = (size_t)WARPS * RING + slack + (slack >= (size_t)WARPS * 1024 ? 0 : (size_t)WARPS * 1024);
     CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, WARPS * 32, smem));
@@ -386,6 +387,13 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     if (!ctx->uploaded) return fail(ctx, NPORE_ERR_STATE, "npore_run before npore_upload");
     if ((flags & NPORE_OUT_NO_EXPANDED) && !(flags & NPORE_OUT_RLE)) return fail(ctx, NPORE_ERR_BAD_ARG, "NO_EXPANDED needs RLE");
     CU(cudaSetDevice(ctx->device));
+    ctx->ran = false;
+    // an error half-way leaves work queued on the stream and events unrecorded: drain it, so that the context is reusable
+    // (upload again or run again) and npore_download reports NPORE_ERR_STATE instead of reading half-written results
+    struct RunGuard {
+        npore_ctx *c; bool ok = false;
+        ~RunGuard() { if (!ok) { cudaStreamSynchronize(c->stream); cudaGetLastError(); c->ran = false; } }
+    } guard{ctx};
     const int n = (int)ctx->items.size();
     const int64_t nchunks = ctx->n_chunks;
     const int NC = 32 * ctx->cpl;
@@ -401,18 +409,22 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     if (want_ops) CU(ctx->d_pack_ops.ensure((size_t)ctx->total_ops + 64));
     if (want_rle) CU(ctx->d_pack_rle.ensure(sizeof(uint32_t) * (size_t)(ctx->total_ops + 64)));
 
-    // ---- sub-batches: greedy over `order` under the scratch budget (sizes from the host-side upper bounds)
-    ctx->slots.assign(nchunks, ChunkSlot{});
-    ctx->subs.clear();
-    size_t max_col = 0, max_row = 0, max_tb = 0;
-    {
+    // ---- sub-batches: greedy over `order` under the scratch budget (sizes from the host-side upper bounds).  The budget is
+    // this context's share of the device (contexts on one device run side by side: PipelinedRealigner); if the scratch still
+    // does not fit (other tenants of the device), the batch is re-cut with half the budget instead of failing.
+    size_t budget = ctx->scratch_budget;
+    if (!ctx->budget_fixed && ctx->device < 64) budget /= (size_t)std::max(1, g_ctx_on_device[ctx->device].load());
+    for (int attempt = 0;; attempt++) {
+        ctx->slots.assign(nchunks, ChunkSlot{});
+        ctx->subs.clear();
+        size_t max_col = 0, max_row = 0, max_tb = 0;
         const size_t per_entry = 32 + 8 + 8 + 4 + 8;   // colrec, relaid, raw_ref, rowrec, raw_seq
         size_t col = 0, row = 0, tb = 0; int first = 0;
         for (int64_t k = 0; k < nchunks; k++) {
             const int bm = ctx->chunk_bmax[ctx->order[k]];
             const size_t ent = (size_t)((bm + NC + 128 + 31) & ~31);
             const size_t need = (col + ent) * per_entry + (tb + bm) * (size_t)(64 * ctx->tbs);
-            if (k > first && need > ctx->scratch_budget) {
+            if (k > first && need > budget) {
                 ctx->subs.push_back({first, (int)(k - first)});
                 max_col = std::max(max_col, col); max_row = std::max(max_row, row); max_tb = std::max(max_tb, tb);
                 col = row = tb = 0; first = (int)k;
@@ -426,10 +438,19 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
             ctx->subs.push_back({first, (int)(nchunks - first)});
             max_col = std::max(max_col, col); max_row = std::max(max_row, row); max_tb = std::max(max_tb, tb);
         }
+        cudaError_t e = ctx->d_colrec.ensure(max_col * 32 + 64);
+        if (e == cudaSuccess) e = ctx->d_relaid.ensure(max_col * 8 + 64);
+        if (e == cudaSuccess) e = ctx->d_raw_ref.ensure(max_col * 8 + 64);
+        if (e == cudaSuccess) e = ctx->d_rowrec.ensure(max_row * 4 + 64);
+        if (e == cudaSuccess) e = ctx->d_raw_seq.ensure(max_row * 8 + 64);
+        if (e == cudaSuccess) e = ctx->d_tb.ensure(max_tb * (size_t)(64 * ctx->tbs) + 256);
+        if (e == cudaSuccess) break;
+        cudaGetLastError();
+        if (e != cudaErrorMemoryAllocation || attempt >= 4 || ctx->subs.size() >= (size_t)std::max<int64_t>(nchunks, 1))
+            return fail(ctx, e == cudaErrorMemoryAllocation ? NPORE_ERR_OOM : NPORE_ERR_CUDA, "scratch allocation", e);
+        ctx->d_tb.release(); ctx->d_colrec.release();          // give back what the failed attempt may have grabbed
+        budget /= 2;
     }
-    CU(ctx->d_colrec.ensure(max_col * 32 + 64)); CU(ctx->d_relaid.ensure(max_col * 8 + 64)); CU(ctx->d_raw_ref.ensure(max_col * 8 + 64));
-    CU(ctx->d_rowrec.ensure(max_row * 4 + 64)); CU(ctx->d_raw_seq.ensure(max_row * 8 + 64));
-    CU(ctx->d_tb.ensure(max_tb * (size_t)(64 * ctx->tbs) + 256));
     int max_sub = 1;
     for (const SubBatch &sb : ctx->subs) max_sub = std::max(max_sub, sb.count);
     int rr_cap = 1;
@@ -595,6 +616,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     S.ms_annotate = ms_ann; S.ms_forward = ms_fwd; S.ms_traceback = ms_tb;
     S.n_sub_batches = (int)ctx->subs.size();
     ctx->ran = true;
+    guard.ok = true;
     return NPORE_OK;
 }
 

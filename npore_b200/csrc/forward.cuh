@@ -102,6 +102,13 @@ __device__ __forceinline__ void lds_pair(uint32_t a, float &v, uint32_t &w)
 __device__ __forceinline__ void sts_slot(uint32_t a, float w0, float w1, float w2, uint32_t w3)
 { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(w0), "f"(w1), "f"(w2), "r"(w3) : "memory"); }
 
+// 16 bytes global -> shared without a register round trip (LDGSTS), L2 only
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{ asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t a)
+{ uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+
 // a ? b : c per bit (one LOP3)
 __device__ __forceinline__ uint32_t bitsel(uint32_t m, uint32_t x, uint32_t y) { return (x & m) | (y & ~m); }
 __device__ __forceinline__ float bitsel_f(uint32_t m, float x, float y) { return __uint_as_float((__float_as_uint(x) & m) | (__float_as_uint(y) & ~m)); }
@@ -157,12 +164,19 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
     const uint32_t smem_base = (smem_raw + RING_BYTES - 1u) & ~(RING_BYTES - 1u);
     {   // the host sizes the dynamic window from the kernel's static size (launch_forward); never run past it
         uint32_t dyn; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
-        if (smem_base + (uint32_t)fwd_warps(CPL) * RING_BYTES > smem_raw + dyn) {
+        const uint32_t front = smem_base - smem_raw;
+        const uint32_t need = front + (uint32_t)fwd_warps(CPL) * RING_BYTES + (front >= (uint32_t)fwd_warps(CPL) * 1024u ? 0u : (uint32_t)fwd_warps(CPL) * 1024u);
+        if (need > dyn) {
             if (threadIdx.x == 0) atomicExch(a.err, 1);
             return;
         }
     }
     const uint32_t wbase = smem_base + (uint32_t)warp * RING_BYTES;
+    // column-record FIFO of the warp (32 records x 32 B, filled by cp.async 16 records ahead of use): in the alignment slack
+    // in front of the rings when it is large enough, else behind them (launch_forward sizes the window the same way)
+    constexpr uint32_t STAGE_BYTES = 32u * 32u;
+    const bool stage_front = smem_base - smem_raw >= (uint32_t)fwd_warps(CPL) * STAGE_BYTES;
+    const uint32_t stbase = (stage_front ? smem_raw : smem_base + (uint32_t)fwd_warps(CPL) * RING_BYTES) + (uint32_t)warp * STAGE_BYTES;
     const uint32_t subbase = (uint32_t)__cvta_generic_to_shared(s_sub);
     const uint32_t m16base = (uint32_t)__cvta_generic_to_shared(s_m16);
 
@@ -264,6 +278,15 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
             for (int t = 0; t < NC / 4; t++)
                 asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%2};" :: "r"(wbase + (uint32_t)(t * 32 + lane) * 16u), "r"(FWD_INF_BITS), "r"(0u) : "memory");
         }
+        {   // prime the column-record FIFO: records [cn, (cn & ~15) + 32), cn = the next column to enter the band
+            const int cn = Dd - r + NC + 1, lim = (cn & ~15) + 32;
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int cf = cn + t * 16 + (lane >> 1);
+                if (cf < lim) cp_async16(stbase + ((uint32_t)cf & 31u) * 32u + (uint32_t)(lane & 1) * 16u, col + 2 * cf + (lane & 1));
+            }
+            cp_async_wait_all();
+        }
         __syncwarp();
         float infd = (float)(100 * (d0 > 0 ? d0 - 1 : 0));   // 100*d, exact in fp32 (d < 2^16); advanced at the top of a step
         uint32_t dsh = (uint32_t)d0 * ROWB;                    // d * ROWB (ring row of this anti-diagonal, before masking)
@@ -297,13 +320,20 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const Forw
                     for (int k = 0; k < CPL; k++) if (es[k] == (0xffffffffu << SH)) rw[k] = nrow;
                 } else {      // 'D': every column moves down one b_col; the one reaching 0 is dead, its slot takes column j+NC
                     Dd++;
+                    const int cnew = Dd - r + NC;                 // the column that takes over the retired slot
 #pragma unroll
                     for (int k = 0; k < CPL; k++) {
                         es[k] -= 1u << SH;
                         if (es[k] == (0xffffffffu << SH)) {
-                            const uint4 *cp = col + 2 * (Dd - r + NC);
-                            ca[k] = cp[0]; cb[k] = cp[1];
+                            const uint32_t sa = stbase + ((uint32_t)cnew & 31u) * 32u;
+                            ca[k] = lds128(sa); cb[k] = lds128(sa + 16u);
                         }
+                    }
+                    if ((cnew & 15) == 15) {      // an aligned batch of 16 records is consumed: refill its FIFO slots, 16 D ops ahead of use
+                        cp_async_wait_all();      // (the batch requested 16 D ops ago, about to be consumed)
+                        __syncwarp();
+                        const int cf = cnew + 17 + (lane >> 1);
+                        cp_async16(stbase + ((uint32_t)cf & 31u) * 32u + (uint32_t)(lane & 1) * 16u, col + 2 * cf + (lane & 1));
                     }
                 }
                 if (!STEADY) hist = ((hist << 1) | o) & 0x3fu;

@@ -27,6 +27,20 @@ class NporeError(RuntimeError):
     pass
 
 
+MAX_ITEM_OPS = (1 << 28) - 1      # include/npore_b200.h: ref_len + seq_len of one item (bit offsets / run-length fields are 28 bits wide)
+
+
+def check_item_sizes(ref_len, seq_len, what="item"):
+    """Raise a per-item error BEFORE a batch is sent: one oversize item would otherwise fail the whole npore_upload with
+    NPORE_ERR_BAD_ARG, valid items included (the reference has no such limit; a 134 Mb haplotype is ours)."""
+    tot = np.asarray(ref_len, dtype=np.int64) + np.asarray(seq_len, dtype=np.int64)
+    bad = np.flatnonzero(tot > MAX_ITEM_OPS)
+    if len(bad):
+        k = int(bad[0])
+        raise NporeError(f"{what} {k}: ref_len + seq_len = {int(tot[k])} exceeds the library limit of {MAX_ITEM_OPS} "
+                         f"(2^28 - 1; a haplotype of ~134 Mb).  Realign this {what} by contig halves or raise the limit in csrc/.")
+
+
 def _pinned(n, dtype):
     """Pinned host array (numpy view of a torch pinned tensor); falls back to pageable if torch has no CUDA."""
     import torch
@@ -300,6 +314,7 @@ class Realigner:
 
     # three-phase API (npore_upload / npore_run / npore_download)
     def upload(self, packed: PackedBatch):
+        check_item_sizes(packed.ref_len, packed.seq_len)
         b = packed.c_struct()
         self._check(self._L.npore_upload(self._ctx, C.byref(b)), "npore_upload")
 
@@ -313,6 +328,7 @@ class Realigner:
 
     def align_packed(self, packed: PackedBatch, flags: int = 0, result: BatchResult = None) -> BatchResult:
         """npore_align_batch: host buffers in, host buffers out."""
+        check_item_sizes(packed.ref_len, packed.seq_len)
         result = result or self.new_result(packed, flags)
         b, r = packed.c_struct(), result.c_struct()
         self._check(self._L.npore_align_batch(self._ctx, C.byref(b), flags, C.byref(r)), "npore_align_batch")
