@@ -143,8 +143,11 @@ __device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uin
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
+#ifndef FWD_MINB
+#define FWD_MINB 1      // min resident CTAs hint for the narrow-band instantiations (register cap = 65536 / (threads * FWD_MINB))
+#endif
 template <int CPL>
-__global__ void __launch_bounds__(fwd_warps(CPL) * 32) forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : 1) forward_kernel(const ForwardArgs a)
 {
     constexpr int NC = 32 * CPL;
     constexpr int TBS = CPL;
