@@ -370,6 +370,7 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
     import threading
     import time
     from .bam import _tables
+    from .scheduler import cut_balanced
     tm = timings if timings is not None else {}
     for k in ("open", "gather", "gpu_wait", "format", "write", "concat"):
         tm.setdefault(k, 0.0)
@@ -393,13 +394,12 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
     shard_load = [0] * G
     done = 0.0
     for (ctg, sel), ld in zip(segs, loads):
-        cs = done + np.cumsum(ld, dtype=np.float64)
-        owner = np.minimum((cs - ld / 2.0) * G / max(total, 1.0), G - 1).astype(np.int64)       # by the read's load midpoint
+        owner = cut_balanced(ld, G, done, total)                   # by the read's load midpoint
         for gidx in np.unique(owner):
             m = owner == gidx
             shard_segs[int(gidx)].append((ctg, sel[m]))
             shard_load[int(gidx)] += int(ld[m].sum())
-        done = float(cs[-1]) if len(cs) else done
+        done += float(ld.sum())
     tm["open"] += time.perf_counter() - t0
     codes, codes_lock = {}, threading.Lock()
     parts = [out if g == 0 else f"{cfg.args.out_prefix}.part{g}.sam" for g in range(G)]

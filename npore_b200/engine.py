@@ -236,13 +236,25 @@ class PackedBatch:
 
 
 class BatchResult:
-    def __init__(self, n, total_ops, n_chunks, want_rle, pinned=True):
+    """Host buffers in the layout of `npore_result`.  want_ops=False leaves out the expanded-ops buffer (NPORE_OUT_NO_EXPANDED);
+    rle_buf / rle_off_buf: caller-owned arrays (uint32 / int64[n+1]) the run-length words and offsets are written into -- e.g.
+    slices of a buffer shared between the per-GPU processes, so that the device-to-host copy IS the gather."""
+
+    def __init__(self, n, total_ops, n_chunks, want_rle, pinned=True, want_ops=True, rle_buf=None, rle_off_buf=None):
         alloc = (lambda m, dt: _pinned(m, dt)[0]) if pinned else (lambda m, dt: np.empty(max(int(m), 1), dtype=dt))
         self.n = n
-        self.ops = alloc(total_ops, np.uint8)
+        self.ops = alloc(total_ops, np.uint8) if want_ops else None
         self.ops_off = np.zeros(n + 1, dtype=np.int64)
-        self.rle = alloc(total_ops if want_rle else 1, np.uint32)
-        self.rle_off = np.zeros(n + 1, dtype=np.int64)
+        if rle_buf is not None:
+            assert rle_buf.dtype == np.uint32 and rle_buf.flags.c_contiguous
+            self.rle = rle_buf
+        else:
+            self.rle = alloc(total_ops if want_rle else 1, np.uint32)
+        if rle_off_buf is not None:
+            assert rle_off_buf.dtype == np.int64 and len(rle_off_buf) >= n + 1 and rle_off_buf.flags.c_contiguous
+            self.rle_off = rle_off_buf
+        else:
+            self.rle_off = np.zeros(n + 1, dtype=np.int64)
         self.chunk_scores = np.zeros(max(n_chunks, 1), dtype=np.float32)
         self.score_off = np.zeros(n + 1, dtype=np.int64)
         self.status = np.zeros(max(n, 1), dtype=np.int32)
@@ -250,7 +262,8 @@ class BatchResult:
 
     def c_struct(self):
         p = lambda a: a.ctypes.data  # noqa: E731
-        return _lib.Result(p(self.ops), len(self.ops), p(self.ops_off),
+        return _lib.Result(p(self.ops) if self.ops is not None else None, len(self.ops) if self.ops is not None else 0,
+                           p(self.ops_off) if self.ops is not None else None,
                            p(self.rle) if self.want_rle else None, len(self.rle), p(self.rle_off) if self.want_rle else None,
                            p(self.chunk_scores), len(self.chunk_scores), p(self.score_off), p(self.status))
 
@@ -310,7 +323,8 @@ class Realigner:
         return int(self._L.npore_count_chunks(self._ctx, packed.n, packed.ref_len.ctypes.data, packed.seq_len.ctypes.data))
 
     def new_result(self, packed: PackedBatch, flags: int, pinned=True) -> BatchResult:
-        return BatchResult(packed.n, packed.total_ops, self.count_chunks(packed), bool(flags & NPORE_OUT_RLE), pinned)
+        return BatchResult(packed.n, packed.total_ops, self.count_chunks(packed), bool(flags & NPORE_OUT_RLE), pinned,
+                           want_ops=not (flags & NPORE_OUT_NO_EXPANDED))
 
     # three-phase API (npore_upload / npore_run / npore_download)
     def upload(self, packed: PackedBatch):

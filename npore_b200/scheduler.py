@@ -6,6 +6,8 @@
   shard_by_region  split coordinate-sorted reads into G contiguous genomic regions of equal cell-update load,
                    one per GPU; no collective: every shard is realigned independently and the
                    host concatenates the per-GPU outputs in region order.
+  cut_balanced     the same cut for items that are ALREADY in (contig, start) order: owner shard of every item, contiguous
+                   and non-decreasing, by the item's load midpoint (bamio.realign_bam_sharded).
 """
 import numpy as np
 
@@ -43,3 +45,14 @@ def shard_by_region(starts, loads, world: int):
     cuts = [int(np.searchsorted(csum, total * g / world, side="right")) for g in range(1, world)]
     bounds = [0] + cuts + [len(order)]
     return [order[bounds[g]:bounds[g + 1]] for g in range(world)]
+
+
+def cut_balanced(loads, world: int, done: float = 0.0, total: float = None):
+    """Owner shard (0 .. world-1) of every item of an ordered list: item k goes to the shard that contains the midpoint of
+    its load interval [csum[k-1], csum[k]) on the axis [0, total) cut into `world` equal parts -- contiguous, non-decreasing,
+    every shard's load within one item of total / world.  `done` / `total` let a caller cut a list that arrives in pieces
+    (one piece per contig): pass the load already seen and the grand total."""
+    loads = np.asarray(loads, dtype=np.float64)
+    cs = done + np.cumsum(loads)
+    tot = float(total if total is not None else (cs[-1] if len(cs) else 0.0))
+    return np.minimum((cs - loads / 2.0) * world / max(tot, 1.0), world - 1).astype(np.int64)

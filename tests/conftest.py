@@ -17,6 +17,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`pytest tests` on a box without a CUDA device: the gpu-marked tests are skipped, not failed (the driver runs the two
+    halves separately with -m "not gpu" / -m gpu; this keeps the unfiltered run green on CPU boxes too)."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:       # noqa: BLE001
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def tables():
     t = np.load(os.path.join(GOLD, "tables.npz"))
