@@ -82,6 +82,15 @@ typedef struct npore_batch {
     int64_t        seq_total;
     const uint32_t *cigar_rle;   /* concatenated BAM-style words                                             */
     const int64_t *cigar_off;    /* [n+1] word offsets                                                       */
+    /* Optional PACKED read bases in BAM's own encoding (SAM spec 4.2.3: 4 bits per base, "=ACMGRSVTWYHKDBN", first base in
+     * the high nibble).  When seq_nib is not NULL, seq_codes / seq_start / seq_total are ignored and item i's read is the
+     * seq_len[i] nibbles starting at nibble seq_nib_start[i] of seq_nib (nibble k lives in byte k/2, high half for even k).
+     * Half the host->device bytes of seq_codes, and the bases of a BAM record go in as they lie in the file: the device
+     * decodes them (replaces the per-character src/cig.pyx:212-229 bases_to_int; A,C,G,T -> 1..4, every other code -> 0 = N,
+     * which is what bases_to_int yields for the IUPAC letters).  Leave all three zero for unpacked input. */
+    const uint8_t *seq_nib;
+    const int64_t *seq_nib_start; /* [n] nibble offsets                                                        */
+    int64_t        seq_nib_bytes; /* bytes in seq_nib                                                          */
 } npore_batch;
 
 typedef struct npore_result {

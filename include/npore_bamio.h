@@ -60,6 +60,13 @@ int      npore_bam_gather(const npore_bam *b, int64_t n_sel, const int64_t *sel,
                           uint8_t *seq_ascii, uint8_t *seq_codes, uint8_t *qual_ascii, const int64_t *seq_off,
                           uint32_t *cigar, const int64_t *cig_off, uint8_t *names, const int64_t *name_off);
 
+/* the selected records' aligned bases in BAM's own 4-bit packing, for npore_batch.seq_nib (include/npore_b200.h): whole bytes are
+ * copied out of the records (soft-clipped ends skipped at byte granularity), nib_start[k] is the nibble offset of record k's first
+ * aligned base inside `nib`.  Two calls: nib == NULL fills byte_off[n_sel+1] (exclusive prefix sum of the bytes per record) so that
+ * the caller can size `nib`; the second call copies.  Replaces the per-base decode of npore_bam_gather's seq_codes on the upload path. */
+int      npore_bam_gather_nib(const npore_bam *b, int64_t n_sel, const int64_t *sel, int n_threads, int64_t *byte_off, uint8_t *nib,
+                              int64_t *nib_start);
+
 /* src/bam.pyx:83 for n records.  ref_names / ref_name_off: concatenated contig names; rle / rle_off: the collapsed CIGAR of
  * every record as (len<<4|op) words (npore_result.rle).  has_qual[i] == 0 or an empty sequence prints '*' for QUAL.
  * Returns the number of bytes written to out (each record ends in '\n'), or a negative code; out_capacity must be at

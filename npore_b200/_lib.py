@@ -16,7 +16,8 @@ class Batch(C.Structure):
     _fields_ = [("n_items", C.c_int32),
                 ("ref_codes", C.c_void_p), ("ref_start", C.c_void_p), ("ref_len", C.c_void_p), ("ref_total", C.c_int64),
                 ("seq_codes", C.c_void_p), ("seq_start", C.c_void_p), ("seq_len", C.c_void_p), ("seq_total", C.c_int64),
-                ("cigar_rle", C.c_void_p), ("cigar_off", C.c_void_p)]
+                ("cigar_rle", C.c_void_p), ("cigar_off", C.c_void_p),
+                ("seq_nib", C.c_void_p), ("seq_nib_start", C.c_void_p), ("seq_nib_bytes", C.c_int64)]
 
 
 class Result(C.Structure):
@@ -50,7 +51,7 @@ EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_set_stream", "npore_c
            "npore_align_batch", "npore_get_np_info", "npore_get_np_info_batch", "npore_confusion_batch", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
 
 IO_EXPORTS = ["npore_io_last_error", "npore_bam_open", "npore_bam_advance", "npore_bam_close", "npore_bam_header_text", "npore_bam_n_refs", "npore_bam_ref",
-              "npore_bam_n_records", "npore_bam_columns", "npore_bam_gather", "npore_sam_bound", "npore_sam_format"]
+              "npore_bam_n_records", "npore_bam_columns", "npore_bam_gather", "npore_bam_gather_nib", "npore_sam_bound", "npore_sam_format"]
 
 _lib = None
 
@@ -99,6 +100,7 @@ def lib():
         L.npore_bam_n_records.restype = C.c_int64
         L.npore_bam_columns.argtypes = [vp] * 11
         L.npore_bam_gather.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.npore_bam_gather_nib.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp, vp]
         L.npore_sam_bound.argtypes = [C.c_int64, vp, vp, vp, C.c_int64]
         L.npore_sam_bound.restype = C.c_int64
         L.npore_sam_format.argtypes = [C.c_int64, C.c_int] + [vp] * 17 + [C.c_int64]

@@ -205,14 +205,28 @@ class NativeBam:
 
     __del__ = close
 
-    def gather(self, sel, n_threads=0, want_qual=True, want_names=True):
+    def gather_nib(self, sel, n_threads=0):
+        """The selected records' aligned bases as they lie in the file (4 bits per base): (nib uint8, nib_start int64[n]) for
+        PackedBatch.from_flat_shared_nib -- no per-base work on the host."""
+        sel = np.ascontiguousarray(sel, dtype=np.int64)
+        boff = np.zeros(len(sel) + 1, np.int64)
+        ps = sel.ctypes.data if len(sel) else None
+        if self._L.npore_bam_gather_nib(self._h, len(sel), ps, n_threads, boff.ctypes.data, None, None):
+            raise RuntimeError(self._L.npore_io_last_error().decode())
+        nib = np.empty(max(int(boff[-1]), 1), np.uint8)
+        start = np.zeros(max(len(sel), 1), np.int64)
+        if self._L.npore_bam_gather_nib(self._h, len(sel), ps, n_threads, boff.ctypes.data, nib.ctypes.data, start.ctypes.data):
+            raise RuntimeError(self._L.npore_io_last_error().decode())
+        return nib[:int(boff[-1])], start[:len(sel)]
+
+    def gather(self, sel, n_threads=0, want_qual=True, want_names=True, want_codes=True):
         """Flat arrays of the selected records: dict with seq_ascii, seq_codes, qual_ascii, seq_off, cigar, cig_off, names,
         name_off (soft clips removed, S/H dropped from the CIGAR; bam.pyx:41-44, 59)."""
         sel = np.ascontiguousarray(sel, dtype=np.int64)
         off = lambda col: np.concatenate(([0], np.cumsum(col[sel], dtype=np.int64)))   # noqa: E731
         o = {"seq_off": off(self.aln_len), "cig_off": off(self.n_cigar), "name_off": off(self.name_len)}
         o["seq_ascii"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8)
-        o["seq_codes"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8)
+        o["seq_codes"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8) if want_codes else None
         o["qual_ascii"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8) if want_qual else None
         o["cigar"] = np.empty(max(int(o["cig_off"][-1]), 1), np.uint32)
         o["names"] = np.empty(max(int(o["name_off"][-1]), 1), np.uint8) if want_names else None
@@ -342,10 +356,11 @@ def _realign_segments(bam, segments, fa, codes, codes_lock, pipe, fh, tm, n_thre
                 stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
                 part = sel[cut:stop]
                 t1 = time.perf_counter()
-                g = bam.gather(part, n_threads)
+                g = bam.gather(part, n_threads, want_codes=False)            # ASCII bases / qualities / names for the SAM text
+                nib, nib_start = bam.gather_nib(part, n_threads)              # the upload: BAM's own 4-bit bases
                 lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
-                packed = PackedBatch.from_flat_shared(cc[lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
-                                                      g["seq_codes"][:int(g["seq_off"][-1])], bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
+                packed = PackedBatch.from_flat_shared_nib(cc[lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
+                                                          nib, nib_start, bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
                 item = (pipe.submit(packed, flags), take_columns(bam, part), g, len(part))
                 tm["gather"] += time.perf_counter() - t1
                 pending.put(item)
@@ -451,7 +466,7 @@ _PIPE_LOCK = _threading.Lock()
 
 
 def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=None, max_batch_ops=64_000_000, n_threads=0,
-                timings=None, window_bytes=64 << 20, n_inflight=2, devices=None):
+                timings=None, window_bytes=16 << 20, n_inflight=2, devices=None):
     """realign.py:75-115 without pysam / Pool: header, ingest, GPU realignment, records appended in input order
     (= coordinate order for a sorted BAM, which is what the header claims).  Returns the number of records written.
     Flat arrays all the way, as a pipeline: the reader streams the file in windows of ~window_bytes of inflated records
@@ -537,10 +552,11 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
                     stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
                     part = sel[cut:stop]
                     t1 = time.perf_counter()
-                    g = bam.gather(part, n_threads)
+                    g = bam.gather(part, n_threads, want_codes=False)        # ASCII bases / qualities / names for the SAM text
+                    nib, nib_start = bam.gather_nib(part, n_threads)          # the upload: BAM's own 4-bit bases
                     lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
-                    packed = PackedBatch.from_flat_shared(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
-                                                          g["seq_codes"][:int(g["seq_off"][-1])], bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
+                    packed = PackedBatch.from_flat_shared_nib(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
+                                                              nib, nib_start, bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
                     item = (pipe.submit(packed, flags), take_columns(bam, part), g, len(part))
                     tm["gather"] += time.perf_counter() - t1
                     pending.put(item)                                        # blocks while n_inflight + 1 batches are unfinished

@@ -82,6 +82,7 @@ struct npore_ctx {
     size_t scratch_budget = 0;
     DevBuf d_sub, d_np;
     // batch-resident
+    DevBuf d_nib, d_nib_start;
     DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
         d_item_len, d_item_status, d_rleA, d_rleB, d_rle_len, d_rle_which, d_ops_off, d_rle_off, d_pack_ops, d_pack_rle, d_order, d_slots, d_counter;
     // per sub-batch scratch
@@ -163,6 +164,22 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
     forward_kernel<CPL><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);
     CU(cudaGetLastError());
     return NPORE_OK;
+}
+
+// BAM 4-bit bases -> base codes (cig.pyx:212-229 on the device): grid (items, parts)
+__global__ void unpack_nib_kernel(const ItemDesc *items, const uint8_t *nib, const int64_t *nib_start, uint8_t *codes, int parts)
+{
+    const ItemDesc &I = items[blockIdx.x];
+    const int per = (I.seq_len + parts - 1) / parts;
+    const int lo = min(I.seq_len, (int)blockIdx.y * per), hi = min(I.seq_len, lo + per);
+    const int64_t ns = nib_start[blockIdx.x];
+    uint8_t *out = codes + I.seq_start;
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        const int64_t k = ns + t;
+        const uint32_t b = nib[k >> 1];
+        const uint32_t v = (k & 1) ? (b & 15u) : (b >> 4);
+        out[t] = v == 1u ? 1 : v == 2u ? 2 : v == 4u ? 3 : v == 8u ? 4 : 0;      // "=ACMGRSVTWYHKDBN": A=1 C=2 G=4 T=8
+    }
 }
 
 }  // namespace
@@ -259,7 +276,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
                       &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
-                      &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
+                      &ctx->d_nib, &ctx->d_nib_start, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
     for (auto *b : bufs) b->release();
     for (auto &b : ctx->d_cm) b.release();
     ctx->d_chunk_dst.release(); ctx->d_part_cnt.release();
@@ -293,23 +310,29 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
 {
     if (!ctx || !b || b->n_items < 0) return NPORE_ERR_BAD_ARG;
     const int n = b->n_items;
-    if (n && (!b->ref_start || !b->ref_len || !b->seq_start || !b->seq_len || !b->cigar_off)) return fail(ctx, NPORE_ERR_BAD_ARG, "null batch array");
+    const bool packed_seq = b->seq_nib != nullptr;
+    if (n && (!b->ref_start || !b->ref_len || !b->seq_len || !b->cigar_off || (packed_seq ? !b->seq_nib_start : !b->seq_start)))
+        return fail(ctx, NPORE_ERR_BAD_ARG, "null batch array");
     CU(cudaSetDevice(ctx->device));
     ctx->uploaded = ctx->ran = false;
     ctx->items.assign(n, ItemDesc{});
-    int64_t out_off = 0, words = 0, nchunks = 0, n_cu = 0;
+    int64_t out_off = 0, words = 0, nchunks = 0, n_cu = 0, seq_run = 0, max_seq = 1;
     for (int i = 0; i < n; i++) {
         ItemDesc &I = ctx->items[i];
         const int64_t rl = b->ref_len[i], sl = b->seq_len[i];
         if (rl < 0 || sl < 0 || rl + sl >= (1ll << 28)) return fail(ctx, NPORE_ERR_BAD_ARG, "item too long (ref_len + seq_len must be < 2^28)");
-        if (b->ref_start[i] < 0 || b->ref_start[i] + rl > b->ref_total || b->seq_start[i] < 0 || b->seq_start[i] + sl > b->seq_total)
-            return fail(ctx, NPORE_ERR_BAD_ARG, "sequence range outside buffer");
+        if (b->ref_start[i] < 0 || b->ref_start[i] + rl > b->ref_total) return fail(ctx, NPORE_ERR_BAD_ARG, "sequence range outside buffer");
+        if (packed_seq) {
+            if (b->seq_nib_start[i] < 0 || b->seq_nib_start[i] + sl > 2 * b->seq_nib_bytes) return fail(ctx, NPORE_ERR_BAD_ARG, "packed read outside buffer");
+        } else if (b->seq_start[i] < 0 || b->seq_start[i] + sl > b->seq_total) return fail(ctx, NPORE_ERR_BAD_ARG, "sequence range outside buffer");
         const int64_t cn = b->cigar_off[i + 1] - b->cigar_off[i];
         if (cn < 0 || cn > 0x7ffffff0ll) return fail(ctx, NPORE_ERR_BAD_ARG, "bad cigar_off");
-        I.ref_start = b->ref_start[i]; I.seq_start = b->seq_start[i];
+        I.ref_start = b->ref_start[i]; I.seq_start = packed_seq ? seq_run : b->seq_start[i];
+        seq_run += sl;
         I.ref_len = (int32_t)rl; I.seq_len = (int32_t)sl;
         I.cig_off = b->cigar_off[i] - b->cigar_off[0]; I.cig_n = (int32_t)cn;
         I.total_ops = (int32_t)(rl + sl);
+        max_seq = std::max<int64_t>(max_seq, sl);
         I.bit_word_off = words; words += (I.total_ops >> 5) + 2;
         I.out_off = out_off; out_off += (I.total_ops + 3) & ~3;      // keep item regions 4-byte aligned
         I.n_chunks = chunks_of(I.total_ops, ctx->P.max_b_rows);
@@ -344,7 +367,12 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
     // device buffers
     CU(ctx->d_items.ensure(sizeof(ItemDesc) * (size_t)std::max(n, 1)));
     CU(ctx->d_ref.ensure((size_t)b->ref_total + 64));
-    CU(ctx->d_seq.ensure((size_t)b->seq_total + 64));
+    const int64_t seq_total = packed_seq ? seq_run : b->seq_total;
+    CU(ctx->d_seq.ensure((size_t)seq_total + 64));
+    if (packed_seq) {
+        CU(ctx->d_nib.ensure((size_t)b->seq_nib_bytes + 64));
+        CU(ctx->d_nib_start.ensure(sizeof(int64_t) * (size_t)std::max(n, 1)));
+    }
     CU(ctx->d_rle.ensure(sizeof(uint32_t) * (size_t)(ctx->total_rle + 1)));
     CU(ctx->d_grp.ensure(sizeof(int32_t) * (size_t)(ctx->total_rle + n + 1)));
     CU(ctx->d_bits.ensure(sizeof(uint32_t) * (size_t)(words + 128)));
@@ -366,7 +394,16 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (n) CU(cudaMemcpyAsync(ctx->d_items.p, ctx->items.data(), sizeof(ItemDesc) * n, cudaMemcpyHostToDevice, ctx->stream));
     if (b->ref_total) CU(cudaMemcpyAsync(ctx->d_ref.p, b->ref_codes, (size_t)b->ref_total, cudaMemcpyHostToDevice, ctx->stream));
-    if (b->seq_total) CU(cudaMemcpyAsync(ctx->d_seq.p, b->seq_codes, (size_t)b->seq_total, cudaMemcpyHostToDevice, ctx->stream));
+    if (packed_seq) {
+        if (b->seq_nib_bytes) CU(cudaMemcpyAsync(ctx->d_nib.p, b->seq_nib, (size_t)b->seq_nib_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (n) {
+            CU(cudaMemcpyAsync(ctx->d_nib_start.p, b->seq_nib_start, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+            const int parts = (int)std::min<int64_t>(64, (max_seq + 65535) / 65536);
+            unpack_nib_kernel<<<dim3(n, parts), 256, 0, ctx->stream>>>(ctx->d_items.as<ItemDesc>(), ctx->d_nib.as<uint8_t>(), ctx->d_nib_start.as<int64_t>(),
+                                                                      ctx->d_seq.as<uint8_t>(), parts);
+            CU(cudaGetLastError());
+        }
+    } else if (b->seq_total) CU(cudaMemcpyAsync(ctx->d_seq.p, b->seq_codes, (size_t)b->seq_total, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->total_rle)
         CU(cudaMemcpyAsync(ctx->d_rle.p, b->cigar_rle + b->cigar_off[0], sizeof(uint32_t) * (size_t)ctx->total_rle, cudaMemcpyHostToDevice, ctx->stream));
     if (nchunks) CU(cudaMemcpyAsync(ctx->d_order.p, ctx->order.data(), sizeof(int32_t) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
@@ -375,7 +412,7 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
     npore_stats &S = ctx->stats;
     S = npore_stats{};
     S.n_items = n; S.n_chunks = nchunks; S.n_cu = n_cu; S.sm_count = ctx->sm_count;
-    S.h2d_bytes = (int64_t)sizeof(ItemDesc) * n + b->ref_total + b->seq_total + 4 * ctx->total_rle + 4 * nchunks;
+    S.h2d_bytes = (int64_t)sizeof(ItemDesc) * n + b->ref_total + (packed_seq ? b->seq_nib_bytes + 8 * (int64_t)n : b->seq_total) + 4 * ctx->total_rle + 4 * nchunks;
     cudaEventElapsedTime(&S.ms_h2d, ctx->ev[0], ctx->ev[1]);
     ctx->uploaded = true;
     return NPORE_OK;

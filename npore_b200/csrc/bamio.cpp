@@ -340,6 +340,34 @@ int npore_bam_gather(const npore_bam *b, int64_t n_sel, const int64_t *sel, int 
     return NPORE_IO_OK;
 }
 
+int npore_bam_gather_nib(const npore_bam *b, int64_t n_sel, const int64_t *sel, int n_threads, int64_t *byte_off, uint8_t *nib, int64_t *nib_start)
+{
+    if (!b || n_sel < 0 || (n_sel && !sel) || !byte_off) return io_fail(NPORE_IO_ERR_ARG, "null argument");
+    for (int64_t k = 0; k < n_sel; k++)
+        if (sel[k] < 0 || (size_t)sel[k] >= b->recs.size()) return io_fail(NPORE_IO_ERR_ARG, "record index out of range");
+    if (!nib) {         // pass 1: bytes needed per record (whole bytes of the record's SEQ that hold an aligned base)
+        byte_off[0] = 0;
+        for (int64_t k = 0; k < n_sel; k++) {
+            const Rec &r = b->recs[(size_t)sel[k]];
+            const int n = r.l_seq - r.lead - r.trail;
+            byte_off[k + 1] = byte_off[k] + (n > 0 ? ((r.lead & 1) + n + 1) / 2 : 0);
+        }
+        return NPORE_IO_OK;
+    }
+    if (!nib_start) return io_fail(NPORE_IO_ERR_ARG, "null argument");
+    parallel_for(n_sel, n_threads, [&](int64_t lo, int64_t hi) {
+        for (int64_t k = lo; k < hi; k++) {
+            const Rec &r = b->recs[(size_t)sel[k]];
+            const uint8_t *rec = &b->data[(size_t)r.off];
+            const uint8_t *sq = rec + 32 + rec[8] + 4 * (size_t)r.n_cigar;
+            const int64_t nb = byte_off[k + 1] - byte_off[k];
+            if (nb > 0) std::memcpy(nib + byte_off[k], sq + (r.lead >> 1), (size_t)nb);      // the bases as they lie in the file
+            nib_start[k] = 2 * byte_off[k] + (r.lead & 1);
+        }
+    });
+    return NPORE_IO_OK;
+}
+
 static inline int dec_len(uint32_t v) { int n = 1; while (v >= 10) { v /= 10; n++; } return n; }
 static inline uint8_t *put_dec(uint8_t *o, int64_t v)
 {

@@ -225,14 +225,33 @@ class PackedBatch:
         words, off = cigars_to_rle_batch(cigars)
         return cls.from_flat(rc, rl, sc, sl, words, off)
 
+    seq_nib = None          # packed reads (BAM 4-bit nibbles) instead of seq_codes: set by from_flat_shared_nib
+
+    @classmethod
+    def from_flat_shared_nib(cls, ref_codes, ref_start, ref_len, seq_nib, seq_nib_start, seq_len, cigar_rle, cigar_off):
+        """Like from_flat_shared, with the reads in BAM's own 4-bit packing (npore_batch.seq_nib): item i's read is the seq_len[i]
+        nibbles from nibble seq_nib_start[i] of seq_nib.  Half the upload bytes; the device decodes (cig.pyx:212-229)."""
+        self = cls.from_flat_shared(ref_codes, ref_start, ref_len, np.zeros(0, np.uint8), seq_len, cigar_rle, cigar_off)
+        self.seq_nib = np.ascontiguousarray(seq_nib, dtype=np.uint8) if len(seq_nib) else np.zeros(1, np.uint8)
+        self.seq_nib_start = np.ascontiguousarray(seq_nib_start, dtype=np.int64)
+        self.seq_nib_bytes = int(len(seq_nib))
+        self.seq_total = int(self.seq_len.astype(np.int64).sum())
+        self.total_ops = int(self.ref_len.astype(np.int64).sum()) + self.seq_total
+        return self
+
     def c_struct(self):
         p = lambda a: a.ctypes.data  # noqa: E731
+        if self.seq_nib is not None:
+            return _lib.Batch(self.n, p(self.ref_codes), p(self.ref_start), p(self.ref_len), self.ref_total,
+                              None, None, p(self.seq_len), 0, p(self.cigar_rle), p(self.cigar_off),
+                              p(self.seq_nib), p(self.seq_nib_start), self.seq_nib_bytes)
         return _lib.Batch(self.n, p(self.ref_codes), p(self.ref_start), p(self.ref_len), self.ref_total,
                           p(self.seq_codes), p(self.seq_start), p(self.seq_len), self.seq_total,
-                          p(self.cigar_rle), p(self.cigar_off))
+                          p(self.cigar_rle), p(self.cigar_off), None, None, 0)
 
     def h2d_bytes(self):
-        return self.ref_total + self.seq_total + 4 * int(self.cigar_off[-1])
+        seq = self.seq_nib_bytes + 8 * self.n if self.seq_nib is not None else self.seq_total
+        return self.ref_total + seq + 4 * int(self.cigar_off[-1])
 
 
 class BatchResult:

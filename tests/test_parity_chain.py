@@ -45,7 +45,7 @@ def test_cuda_vs_compiled_reference_direct(tables):
         rf, sq, cg, r, mb = synth.fuzz_case(rng, cm)
         groups.setdefault((r, mb), []).append((rf, sq, cg))
     big_ref, tr = synth.make_reference_with_tracts(200_000, rng)
-    for rd in synth.make_reads(big_ref, 6, 10_000, rng, cm, tracts=tr):      # defaults: a 19,999-row chunk + a tail chunk
+    for rd in synth.make_reads(big_ref, 6, 10_400, rng, cm, tracts=tr):      # defaults: a 19,999-row chunk + a tail chunk
         groups.setdefault((30, 20000), []).append((rd[9], rd[7], cig.expand_cigar(rd[5])))
     n = two_chunk = 0
     for (r, mb), cases in groups.items():
