@@ -68,13 +68,14 @@ int      npore_bam_gather_nib(const npore_bam *b, int64_t n_sel, const int64_t *
                               int64_t *nib_start);
 
 /* src/bam.pyx:83 for n records.  ref_names / ref_name_off: concatenated contig names; rle / rle_off: the collapsed CIGAR of
- * every record as (len<<4|op) words (npore_result.rle).  has_qual[i] == 0 or an empty sequence prints '*' for QUAL.
+ * every record as (len<<4|op) words (npore_result.rle).  has_qual[i] == 0 or an empty sequence prints '*' for QUAL; a ref_id outside
+ * [0, n_refs) prints '*' for RNAME.
  * Returns the number of bytes written to out (each record ends in '\n'), or a negative code; out_capacity must be at
  * least npore_sam_bound(...). */
 int64_t  npore_sam_bound(int64_t n, const int64_t *name_off, const int64_t *seq_off, const int64_t *rle_off, int64_t max_ref_name);
 int64_t  npore_sam_format(int64_t n, int n_threads,
                           const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
-                          const uint8_t *ref_names, const int64_t *ref_name_off,
+                          const uint8_t *ref_names, const int64_t *ref_name_off, int32_t n_refs,
                           const int32_t *pos, const int32_t *end, const int32_t *mapq,
                           const uint32_t *rle, const int64_t *rle_off,
                           const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,

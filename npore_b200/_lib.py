@@ -103,7 +103,7 @@ def lib():
         L.npore_bam_gather_nib.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp, vp]
         L.npore_sam_bound.argtypes = [C.c_int64, vp, vp, vp, C.c_int64]
         L.npore_sam_bound.restype = C.c_int64
-        L.npore_sam_format.argtypes = [C.c_int64, C.c_int] + [vp] * 17 + [C.c_int64]
+        L.npore_sam_format.argtypes = [C.c_int64, C.c_int] + [vp] * 6 + [C.c_int32] + [vp] * 11 + [C.c_int64]
         L.npore_sam_format.restype = C.c_int64
         _lib = L
     return _lib

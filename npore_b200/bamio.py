@@ -257,7 +257,7 @@ def format_sam(bam, sel, g, rle, rle_off, n_threads=0, cols=None):
     if g["qual_ascii"] is None:
         hq = np.zeros_like(hq)
     got = L.npore_sam_format(n, n_threads, g["names"].ctypes.data, g["name_off"].ctypes.data, flag.ctypes.data, ref_id.ctypes.data,
-                             rn.ctypes.data, rn_off.ctypes.data, pos.ctypes.data, end.ctypes.data, mapq.ctypes.data,
+                             rn.ctypes.data, rn_off.ctypes.data, len(bam.refs), pos.ctypes.data, end.ctypes.data, mapq.ctypes.data,
                              rle.ctypes.data if len(rle) else None, rle_off.ctypes.data, g["seq_ascii"].ctypes.data, qual.ctypes.data,
                              g["seq_off"].ctypes.data, hq.ctypes.data, hp.ctypes.data, out.ctypes.data, cap)
     if got < 0:

@@ -122,6 +122,7 @@ static int load_blocks(npore_bam *b, size_t want)
         if (std::fread(&cbuf[at], 1, rest, b->fh) != rest) return io_fail(NPORE_IO_ERR_FORMAT, "truncated BGZF member");
         Blk k;
         k.coff = at; k.clen = rest - 8; k.crc = rd32(&cbuf[at + rest - 8]); k.ulen = rd32(&cbuf[at + rest - 4]); k.uoff = base + added;
+        if (k.ulen > 65536) return io_fail(NPORE_IO_ERR_FORMAT, "BGZF member claims more than 64 KiB of data (SAM spec 4.1: ISIZE <= 65536)");
         added += k.ulen;
         blks.push_back(k);
     }
@@ -225,10 +226,13 @@ int64_t npore_bam_advance(npore_bam *bam, int64_t max_bytes)
             o.name_len = r[8] ? r[8] - 1 : 0; o.mapq = r[9];
             o.n_cigar = rd16(r + 12); o.flag = rd16(r + 14); o.l_seq = (int32_t)rd32(r + 16);
             const uint8_t *cg = r + 32 + r[8];
+            const uint8_t *end = r + bs;
+            // malformed record (negative l_seq, or fields running past block_size): treated as empty -- checked BEFORE any pointer is formed
+            if (o.l_seq < 0 || 32 + (size_t)r[8] + 4 * (size_t)o.n_cigar + ((size_t)o.l_seq + 1) / 2 + (size_t)o.l_seq > bs) { o.n_cigar = 0; o.l_seq = 0; }
             const uint8_t *sq = cg + 4 * (size_t)o.n_cigar;
             const uint8_t *ql = sq + ((size_t)o.l_seq + 1) / 2;
-            const uint8_t *aux = ql + o.l_seq, *end = r + bs;
-            if (aux > end) { o.n_cigar = 0; o.l_seq = 0; aux = end; }          // malformed record: treated as empty
+            const uint8_t *aux = ql + o.l_seq;
+            if (aux > end) aux = end;
             int64_t span = 0; int kept = 0;
             for (int c = 0; c < o.n_cigar; c++) {
                 const uint32_t w = rd32(cg + 4 * c), op = w & 15u;
@@ -388,7 +392,7 @@ int64_t npore_sam_bound(int64_t n, const int64_t *name_off, const int64_t *seq_o
 
 int64_t npore_sam_format(int64_t n, int n_threads,
                          const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
-                         const uint8_t *ref_names, const int64_t *ref_name_off,
+                         const uint8_t *ref_names, const int64_t *ref_name_off, int32_t n_refs,
                          const int32_t *pos, const int32_t *end, const int32_t *mapq,
                          const uint32_t *rle, const int64_t *rle_off,
                          const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
@@ -408,7 +412,8 @@ int64_t npore_sam_format(int64_t n, int n_threads,
             int64_t len = 12;                                         // 11 tabs + '\n'
             len += name_off[k + 1] - name_off[k];
             len += put_dec(tmp, flag[k]) - tmp;
-            len += ref_name_off[ref_id[k] + 1] - ref_name_off[ref_id[k]];
+            const bool rok = ref_id[k] >= 0 && ref_id[k] < n_refs;        // a record without a (valid) reference prints RNAME '*'
+            len += rok ? ref_name_off[ref_id[k] + 1] - ref_name_off[ref_id[k]] : 1;
             len += put_dec(tmp, (int64_t)pos[k] + 1) - tmp;
             len += put_dec(tmp, mapq[k]) - tmp;
             for (int64_t g = rle_off[k]; g < rle_off[k + 1]; g++) len += dec_len(rle[g] >> 4) + 1;
@@ -429,8 +434,11 @@ int64_t npore_sam_format(int64_t n, int n_threads,
             const int64_t nl = name_off[k + 1] - name_off[k];
             std::memcpy(o, names + name_off[k], (size_t)nl); o += nl; *o++ = '\t';
             o = put_dec(o, flag[k]); *o++ = '\t';
-            const int64_t rl = ref_name_off[ref_id[k] + 1] - ref_name_off[ref_id[k]];
-            std::memcpy(o, ref_names + ref_name_off[ref_id[k]], (size_t)rl); o += rl; *o++ = '\t';
+            if (ref_id[k] >= 0 && ref_id[k] < n_refs) {
+                const int64_t rl = ref_name_off[ref_id[k] + 1] - ref_name_off[ref_id[k]];
+                std::memcpy(o, ref_names + ref_name_off[ref_id[k]], (size_t)rl); o += rl;
+            } else *o++ = '*';
+            *o++ = '\t';
             o = put_dec(o, (int64_t)pos[k] + 1); *o++ = '\t';
             o = put_dec(o, mapq[k]); *o++ = '\t';
             for (int64_t g = rle_off[k]; g < rle_off[k + 1]; g++) { o = put_dec(o, rle[g] >> 4); *o++ = (uint8_t)kOps[rle[g] & 15u]; }

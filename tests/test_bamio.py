@@ -223,3 +223,64 @@ def test_realign_bam_end_to_end(golden, tables, tmp_path):
     assert n3 == len(reads) and body4 == [want[r[0]] for r in reads]
     n4 = bamio.realign_bam(bam, fasta, out_prefix=str(tmp_path / "out5"), argv=["x"], window_bytes=3000, max_reads=4)
     assert n4 == 4 and [l for l in open(str(tmp_path / "out5.sam")).read().splitlines() if not l.startswith("@")] == [want[r[0]] for r in reads[:4]]
+
+
+def test_gather_nib_is_the_file_packing(tmp_path):
+    """npore_bam_gather_nib: the aligned bases as they lie in the record (4 bits each, soft clips skipped) -- decoding the nibbles
+    with the table of include/npore_b200.h gives npore_bam_gather's seq_codes."""
+    rng = np.random.default_rng(12)
+    recs = []
+    for k in range(60):
+        n = int(rng.integers(0, 90))
+        lead, trail = (int(rng.integers(0, 6)), int(rng.integers(0, 6))) if n > 12 else (0, 0)
+        seq = "".join(rng.choice(list("ACGTNRY"), size=n))
+        cig = ([(lead, "S")] if lead else []) + ([(n - lead - trail, "M")] if n - lead - trail else []) + ([(trail, "S")] if trail else [])
+        recs.append({"name": f"r{k}", "flag": 0, "ref_id": 0, "pos": 10 * k, "mapq": 9, "cigar": cig, "seq": seq, "qual": None, "tags": {}})
+    path = str(tmp_path / "n.bam")
+    bamio.write_bam(path, "@HD\tVN:1.6\n", [("a", 5000)], recs)
+    nb = bamio.NativeBam(path)
+    sel = np.arange(nb.n)[::-1].copy()                    # any order
+    g = nb.gather(sel)
+    nib, start = nb.gather_nib(sel)
+    lut = np.zeros(16, np.uint8); lut[[1, 2, 4, 8]] = [1, 2, 3, 4]
+    for k in range(len(sel)):
+        n = int(g["seq_off"][k + 1] - g["seq_off"][k])
+        idx = start[k] + np.arange(n)
+        b = nib[idx >> 1] if n else np.zeros(0, np.uint8)
+        v = np.where(idx & 1, b & 15, b >> 4)
+        assert np.array_equal(lut[v], g["seq_codes"][g["seq_off"][k]:g["seq_off"][k + 1]])
+    nb.close()
+
+
+def test_malformed_inputs_are_rejected_not_read_out_of_bounds(tmp_path):
+    """a record with l_seq < 0 is treated as empty, a BGZF member claiming > 64 KiB is a format error, and
+    npore_sam_format prints RNAME '*' for a ref_id outside the header's contigs."""
+    import struct
+    from npore_b200 import _lib
+    recs = [{"name": "ok", "flag": 0, "ref_id": 0, "pos": 5, "mapq": 1, "cigar": [(4, "M")], "seq": "ACGT", "qual": None, "tags": {}}]
+    path = str(tmp_path / "m.bam")
+    bamio.write_bam(path, "@HD\tVN:1.6\n", [("a", 100)], recs)
+    # rebuild the stream by hand with l_seq = -5 in the record
+    body = bytearray()
+    text = b"@HD\tVN:1.6\n"
+    body += b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", 1) + struct.pack("<i", 2) + b"a\0" + struct.pack("<i", 100)
+    rec = struct.pack("<iiBBHHHiiii", 0, 5, 3, 1, 0, 0, 0, -5, -1, -1, 0) + b"ok\0"
+    body += struct.pack("<i", len(rec)) + rec
+    with open(path, "wb") as fh:
+        fh.write(bamio._bgzf_block(bytes(body))); fh.write(bamio._bgzf_block(b""))
+    nb = bamio.NativeBam(path)
+    assert nb.n == 1 and int(nb.aln_len[0]) == 0 and int(nb.n_cigar[0]) == 0
+    g = nb.gather(np.arange(1))
+    # ref_id out of range -> '*'
+    cols = bamio.take_columns(nb, np.arange(1)); cols["ref_id"][:] = 7
+    blob = bamio.format_sam(nb, None, g, np.zeros(1, np.uint32), np.zeros(2, np.int64), cols=cols).tobytes().decode()
+    assert blob.split("\t")[2] == "*"
+    nb.close()
+    # ISIZE > 64 KiB
+    blk = bytearray(bamio._bgzf_block(b"x" * 100))
+    blk[-4:] = struct.pack("<I", 1 << 20)
+    with open(path, "wb") as fh:
+        fh.write(bytes(blk))
+    with pytest.raises(ValueError):
+        bamio.NativeBam(path)
+    assert "npore_bam_gather_nib" in _lib.IO_EXPORTS
