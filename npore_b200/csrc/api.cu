@@ -159,6 +159,9 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
         CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     ctx->stats.fwd_warps_per_sm = per_sm * WARPS;
+    if (getenv("NPORE_DEBUG"))
+        fprintf(stderr, "[npore] forward_kernel<%d>: %d warps/CTA, %zu B dynamic + %zu B static shared, %d regs, %d CTAs/SM\n", CPL, WARPS, smem,
+                (size_t)fattr.sharedSizeBytes, fattr.numRegs, per_sm);
     int grid = std::min((n_sub + WARPS - 1) / WARPS, ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
     forward_kernel<CPL><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);

@@ -144,10 +144,11 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
 #ifndef FWD_MINB
-#define FWD_MINB 1      // min resident CTAs hint for the narrow-band instantiations (register cap = 65536 / (threads * FWD_MINB))
+#define FWD_MINB 4      // min resident CTAs of the narrow-band instantiations: caps ptxas at 128 registers (4 CTAs x 4 warps per SM);
+                        // with a hint of 1 it takes 164 and only 3 CTAs fit (measured: 29.0 instead of 26.7 ms per C2 step)
 #endif
 template <int CPL>
-__global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : 1) forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL == 4 ? 2 : 1) forward_kernel(const ForwardArgs a)
 {
     constexpr int NC = 32 * CPL;
     constexpr int TBS = CPL;
