@@ -243,8 +243,7 @@ def file_e2e(ref, reads, S, NP, steps, warmup, devices=None):
         for s in range(warmup + steps):
             tm = {}
             t0 = time.perf_counter()
-            got = bamio.realign_bam(os.path.join(d, "in.bam"), fa, out_prefix=out, argv=["bench.py"], timings=tm, devices=devices,
-                                    max_batch_ops=16_000_000)
+            got = bamio.realign_bam(os.path.join(d, "in.bam"), fa, out_prefix=out, argv=["bench.py"], timings=tm, devices=devices)
             dt = time.perf_counter() - t0
             if s >= warmup:
                 times.append(dt)
