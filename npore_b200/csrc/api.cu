@@ -718,7 +718,8 @@ int npore_get_np_info_batch(npore_ctx *ctx, int32_t n_seqs, const uint8_t *codes
         if (off[i + 1] < off[i] || off[i + 1] - off[i] > 0x7ffffff0ll) return fail(ctx, NPORE_ERR_BAD_ARG, "bad sequence offsets");
     if (total == 0) return NPORE_OK;
     CU(cudaSetDevice(ctx->device));
-    DevBuf d_s, d_off, d_raw, d_out, d_e;
+    // staging lives in the context (grow-only, shared with npore_confusion_batch's slots): no cudaMalloc / cudaFree per call
+    DevBuf &d_s = ctx->d_cm[4], &d_off = ctx->d_cm[3], &d_raw = ctx->d_cm[5], &d_out = ctx->d_cm[21], &d_e = ctx->d_cm[6];
     const size_t ob = (size_t)total * 2 * ctx->P.max_n * sizeof(int32_t);
     int rc = NPORE_OK;
     if (d_s.ensure((size_t)total) != cudaSuccess || d_off.ensure(sizeof(int64_t) * (size_t)(n_seqs + 1)) != cudaSuccess ||
@@ -737,7 +738,6 @@ int npore_get_np_info_batch(npore_ctx *ctx, int32_t n_seqs, const uint8_t *codes
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) rc = fail(ctx, NPORE_ERR_CUDA, "np_info", e);
     }
-    d_s.release(); d_off.release(); d_raw.release(); d_out.release(); d_e.release();
     return rc;
 }
 

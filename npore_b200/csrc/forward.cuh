@@ -134,7 +134,11 @@ __device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uin
     lds_pair(ad, base, w);
     const uint32_t xs = w & C;                                        // SHR.RUN << 16 of the source, 0 at a tract start
     const uint32_t q = __umulhi(xs, B);                               // trunc(run / n) <= NP_RUN_SAT < NP_TABQ
+#if FWD_TAB_PROBE      // timing probe only (results are wrong): every lookup hits one cache line = the bound on what staging the table could buy
+    const float cand = base + __ldg(tabS + ((q * trows + (A & 0xffffu)) & 7u));
+#else
     const float cand = base + __ldg(tabS + (q * trows + (A & 0xffffu)));
+#endif
     const bool better = ok && cand < Sv;
     const uint32_t nr = __viaddmin_u32(xs, A & 0x70000u, FWD_SAT16);
     Sv = better ? cand : Sv; Sb = better ? base : Sb; Sr = better ? nr : Sr;
@@ -143,6 +147,9 @@ __device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uin
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
+#ifndef FWD_TAB_PROBE
+#define FWD_TAB_PROBE 0
+#endif
 #ifndef FWD_MINB
 #define FWD_MINB 4      // min resident CTAs of the narrow-band instantiations: caps ptxas at 128 registers (4 CTAs x 4 warps per SM);
                         // with a hint of 1 it takes 164 and only 3 CTAs fit (measured: 29.0 instead of 26.7 ms per C2 step)
