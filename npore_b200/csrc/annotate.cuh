@@ -45,6 +45,7 @@ struct AnnotateArgs {
     uint8_t *raw_ref, *raw_seq;    // 8 B per entry
     uint4 *colrec; uint2 *relaid; uint32_t *rowrec;
     int max_n, max_l, nc, inf_row;      // inf_row = max_n * (max_l + 1)
+    int e6_stride;                      // words per period in the dynamic shared window (0: none)
 };
 
 // np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
@@ -53,25 +54,45 @@ struct AnnotateArgs {
 // (fewer than n => it heads a phase chain) and where its run ends; (3) chain heads write their chain.  Chains of one
 // period write disjoint bytes, so two barriers per period suffice (the `longest` test reads bytes of smaller periods).
 #define ANN_MAX_WORDS 2048          // 65536 positions (max_b_rows <= 65000)
+// e6 (optional): dynamic shared memory for the equality words of ALL periods, NP_MAXN planes of `e6_stride` words (>= nwords + 2).
+// With it the slice is read once (7 bytes per position instead of 2 per position and period) and every period costs one barrier
+// instead of two; without it (long stand-alone sequences, callers without the dynamic window) the words are recomputed per period.
 __device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n, int max_l, uint8_t *raw, int32_t *full_out,
-                               uint32_t *ebits_long = nullptr)
+                               uint32_t *ebits_long = nullptr, uint32_t *e6 = nullptr, int e6_stride = 0)
 {
     __shared__ uint32_t s_e_smem[ANN_MAX_WORDS + 2];
-    uint32_t *s_e = ebits_long ? ebits_long : s_e_smem;         // long stand-alone sequences keep the words in global memory
     const int tid = threadIdx.x, lane = tid & 31;
     for (int q = tid; q < len; q += ANN_THREADS) reinterpret_cast<uint2 *>(raw)[q] = make_uint2(0u, 0u);
     if (full_out) for (int q = tid; q < len * 2 * max_n; q += ANN_THREADS) full_out[q] = 0;
     const int nwords = (len + 31) >> 5;
-    __syncthreads();
-    for (int n = 1; n <= max_n; n++) {
+    const bool all_periods = e6 != nullptr && !ebits_long && e6_stride >= nwords + 2;
+    if (all_periods) {
         for (int base = (tid >> 5) << 5; base < nwords * 32; base += ANN_THREADS) {
             const int q = base + lane;
-            const bool e = (q + n < len) && (s[q] == s[q + n]);
-            const uint32_t bits = __ballot_sync(NP_FULL, e);
-            if (lane == 0) s_e[base >> 5] = bits;
+            uint32_t c[NP_MAXN + 1];
+#pragma unroll
+            for (int t = 0; t <= NP_MAXN; t++) c[t] = (q + t < len) ? (uint32_t)s[q + t] : 0xffu + (uint32_t)t;      // past the end: equal to nothing
+#pragma unroll
+            for (int n = 1; n <= NP_MAXN; n++) {
+                const uint32_t bits = __ballot_sync(NP_FULL, c[0] == c[n]);
+                if (lane == 0) e6[(n - 1) * e6_stride + (base >> 5)] = bits;
+            }
         }
-        if (tid == 0) s_e[nwords] = 0u;
-        __syncthreads();
+        if (tid < NP_MAXN) { e6[tid * e6_stride + nwords] = 0u; e6[tid * e6_stride + nwords + 1] = 0u; }
+    }
+    __syncthreads();
+    for (int n = 1; n <= max_n; n++) {
+        uint32_t *s_e = ebits_long ? ebits_long : all_periods ? e6 + (n - 1) * e6_stride : s_e_smem;      // long stand-alone sequences: global memory
+        if (!all_periods) {
+            for (int base = (tid >> 5) << 5; base < nwords * 32; base += ANN_THREADS) {
+                const int q = base + lane;
+                const bool e = (q + n < len) && (s[q] == s[q + n]);
+                const uint32_t bits = __ballot_sync(NP_FULL, e);
+                if (lane == 0) s_e[base >> 5] = bits;
+            }
+            if (tid == 0) s_e[nwords] = 0u;
+            __syncthreads();
+        }
         for (int h = tid; h < len; h += ANN_THREADS) {
             const int w = h >> 5, b = h & 31;
             const uint32_t cur = s_e[w];
@@ -188,11 +209,12 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
     const ChunkSlot sl = a.slots[ci];
     if (!c.valid) return;
     const ItemDesc &I = a.items[c.item];
+    extern __shared__ uint32_t ann_e6[];                 // NP_MAXN planes of a.e6_stride equality words
     if (side == 0) {
         const int len = c.rlen;
         const uint8_t *s = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
         uint8_t *raw = a.raw_ref + sl.col_off * 8;
-        annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr);
+        annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr, nullptr, a.e6_stride ? ann_e6 : nullptr, a.e6_stride);
         uint4 *out = a.colrec + 2 * sl.col_off;
         uint2 *rel = a.relaid + sl.col_off;
         const int NC = a.nc, CPL = NC / 32;
@@ -243,7 +265,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         const int len = c.slen;
         const uint8_t *s = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
         uint8_t *raw = a.raw_seq + sl.row_off * 8;
-        annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr);
+        annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr, nullptr, a.e6_stride ? ann_e6 : nullptr, a.e6_stride);
         uint32_t *out = a.rowrec + sl.row_off;
         for (int i = threadIdx.x; i < sl.row_cap; i += ANN_THREADS) {
             uint32_t v = 0;

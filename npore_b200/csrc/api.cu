@@ -535,7 +535,14 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         aa.colrec = ctx->d_colrec.as<uint4>(); aa.relaid = ctx->d_relaid.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
         aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.inf_row = ctx->P.np_rows;
         CU(cudaEventRecord(e0, ctx->stream));
-        annotate_kernel<<<2 * sb.count, ANN_THREADS, 0, ctx->stream>>>(aa);
+        {   // equality words of all periods in dynamic shared memory: 6 planes of (longest slice / 32 + 2) words
+            int bm = 1;
+            for (int k = 0; k < sb.count; k++) bm = std::max(bm, ctx->chunk_bmax[ctx->order[sb.first + k]]);
+            aa.e6_stride = (bm + 1 + 31) / 32 + 2;
+            const size_t dyn = (size_t)NP_MAXN * aa.e6_stride * sizeof(uint32_t);
+            if (dyn > 48 * 1024) CU(cudaFuncSetAttribute(annotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            annotate_kernel<<<2 * sb.count, ANN_THREADS, dyn, ctx->stream>>>(aa);
+        }
         CU(cudaGetLastError()); S.launches++;
         CU(cudaEventRecord(e1, ctx->stream));
 
