@@ -46,6 +46,7 @@ struct AnnotateArgs {
     uint4 *colrec; uint2 *relaid; uint32_t *rowrec;
     int max_n, max_l, nc, inf_row;      // inf_row = max_n * (max_l + 1)
     int e6_stride;                      // words per period in the dynamic shared window (0: none)
+    int cpl;                            // cells per lane of the forward instantiation that will read the records (ring position of a slot)
 };
 
 // np_info of one slice into raw (and optionally the reference's int32 [len][2][max_n] array).
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         annotate_slice(s, len, a.max_n, a.max_l, raw, nullptr, nullptr, a.e6_stride ? ann_e6 : nullptr, a.e6_stride);
         uint4 *out = a.colrec + 2 * sl.col_off;
         uint2 *rel = a.relaid + sl.col_off;
-        const int NC = a.nc, CPL = NC / 32;
+        const int NC = a.nc, CPL = a.cpl, PER = NC / CPL;      // slot s sits at ring position (s % CPL) * PER + s / CPL (forward.cuh)
         for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
             uint2 v = make_uint2(0u, 0u);
             const uint32_t empty = (uint32_t)a.inf_row;       // "no candidate": the all-INF table row; the source it reads is irrelevant
@@ -230,10 +231,9 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                     if (n <= 4) v.x |= b << (8 * (n - 1)); else v.y |= b << (8 * (n - 5));
                     const uint32_t L = b & 0x7fu;
                     if (L) {
-                        // byte offset inside one warp's ring [NP_RING rows][NC positions][16 B]; slot s sits at position
-                        // (s % CPL)*32 + s / CPL; pair 0 = {MAT.VAL, -}, pair 1 = {SHR run-start value, runs}
+                        // byte offset inside one ring [NP_RING rows][NC positions][16 B]; pair 0 = {MAT.VAL, -}, pair 1 = {SHR run-start value, runs}
                         const uint32_t ss = (uint32_t)(j - n) & (uint32_t)(NC - 1);
-                        const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (uint32_t)(NC * 16) + ((ss % CPL) * 32u + ss / CPL) * 16u + ((b & 0x80u) ? 0u : 8u);
+                        const uint32_t F = (uint32_t)((-n) & (NP_RING - 1)) * (uint32_t)(NC * 16) + ((ss % CPL) * (uint32_t)PER + ss / CPL) * 16u + ((b & 0x80u) ? 0u : 8u);
                         if (nshr < 2) {
                             sA[nshr] = ((F | (uint32_t)n) << 16) | (uint32_t)((n - 1) * (a.max_l + 1) + (int)L);
                             sB[nshr] = (65536u + (uint32_t)n - 1u) / (uint32_t)n;

@@ -131,42 +131,55 @@ inline int chunks_of(int total, int max_b_rows)
     return total > 0 ? (total + step - 1) / step : 0;
 }
 
-template <int CPL>
+template <int CPL, int T>
 int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 {
-    constexpr int WARPS = fwd_warps(CPL);
-    // rings are aligned to their size inside the CTA's shared window (cell address = offset | base).  The dynamic window
-    // starts after the per-CTA reservation and the kernel's static arrays, so the slack needed is known exactly; the kernel
-    // re-derives it from the real addresses and raises ctl[3] instead of running past the window.
-    constexpr size_t RING = (size_t)NP_RING * 32 * CPL * 16;
+    constexpr int WARPS = fwd_warps(CPL, T), TEAMS = WARPS / T;
+    // rings (one per team of T warps) are aligned to their size inside the CTA's shared window (cell address = offset | base).
+    // The dynamic window starts after the per-CTA reservation and the kernel's static arrays, so the slack needed is known
+    // exactly; the kernel re-derives it from the real addresses and raises the error flag instead of running past the window.
+    constexpr size_t RING = (size_t)NP_RING * 32 * CPL * T * 16;
     cudaFuncAttributes fattr;
-    CU(cudaFuncGetAttributes(&fattr, forward_kernel<CPL>));
+    CU(cudaFuncGetAttributes(&fattr, forward_kernel<CPL, T>));
     int reserved = 1024;
     cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device);
     const size_t start = (size_t)reserved + fattr.sharedSizeBytes;
     const size_t slack = (RING - start % RING) % RING;
     // + the per-warp column-record FIFOs (1 KB each): inside the slack when it is large enough, else behind the rings
-    const size_t smem = (size_t)WARPS * RING + slack + (slack >= (size_t)WARPS * 1024 ? 0 : (size_t)WARPS * 1024);
-    CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)TEAMS * RING + slack + (slack >= (size_t)WARPS * 1024 ? 0 : (size_t)WARPS * 1024);
+    CU(cudaFuncSetAttribute(forward_kernel<CPL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL>, WARPS * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL, T>, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     {   // ask for the smallest shared-memory carve-out that holds the resident CTAs: the rest of the 256 KB is L1 for the
         // score-table lookups (the default picked 196 KB where 164 KB is enough, leaving 56 instead of 92 KB of L1)
         const size_t need = (size_t)per_sm * (smem + fattr.sharedSizeBytes + reserved);
         int pct = (int)((need * 100 + 233472 - 1) / 233472);
         if (pct > 100) pct = 100;
-        CU(cudaFuncSetAttribute(forward_kernel<CPL>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        CU(cudaFuncSetAttribute(forward_kernel<CPL, T>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     ctx->stats.fwd_warps_per_sm = per_sm * WARPS;
     if (getenv("NPORE_DEBUG"))
-        fprintf(stderr, "[npore] forward_kernel<%d>: %d warps/CTA, %zu B dynamic + %zu B static shared, %d regs, %d CTAs/SM\n", CPL, WARPS, smem,
-                (size_t)fattr.sharedSizeBytes, fattr.numRegs, per_sm);
-    int grid = std::min((n_sub + WARPS - 1) / WARPS, ctx->sm_count * per_sm);
+        fprintf(stderr, "[npore] forward_kernel<%d,%d>: %d warps/CTA, %zu B dynamic + %zu B static shared, %d regs, %d CTAs/SM, %d chunks\n", CPL, T, WARPS, smem,
+                (size_t)fattr.sharedSizeBytes, fattr.numRegs, per_sm, n_sub);
+    int grid = std::min((n_sub + TEAMS - 1) / TEAMS, ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
-    forward_kernel<CPL><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);
+    forward_kernel<CPL, T><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);
     CU(cudaGetLastError());
     return NPORE_OK;
+}
+
+// Which instantiation runs a sub-batch of n chunks at band slots NC = 32 * nc32: one chunk per warp, or a team of two warps per
+// chunk (forward.cuh) -- for bands wider than 128 cells always (<4,2> instead of the 255-register <8,1>), otherwise when the
+// sub-batch has fewer chunks than half the warp slots of the one-warp form (latency-bound launches: C1, 50 k-row windows,
+// small file batches).  NPORE_TEAM=0/1 forces the choice (tests, A/B).
+inline int forward_team(const npore_ctx *ctx, int nc32, int n_sub)
+{
+    if (nc32 == 1) return 1;
+    if (const char *e = getenv("NPORE_TEAM")) { const int t = atoi(e); if (t == 1 || t == 2) return nc32 == 8 && t == 1 ? 1 : t; }
+    if (nc32 == 8) return 2;
+    const int slots = ctx->sm_count * (nc32 == 2 ? 16 : 12);          // resident one-warp chunks of <2,1> / <4,1>
+    return 2 * n_sub <= slots ? 2 : 1;
 }
 
 // BAM 4-bit bases -> base codes (cig.pyx:212-229 on the device): grid (items, parts)
@@ -534,6 +547,8 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         aa.raw_ref = ctx->d_raw_ref.as<uint8_t>(); aa.raw_seq = ctx->d_raw_seq.as<uint8_t>();
         aa.colrec = ctx->d_colrec.as<uint4>(); aa.relaid = ctx->d_relaid.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
         aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.inf_row = ctx->P.np_rows;
+        const int team = forward_team(ctx, ctx->cpl, sb.count);       // warps per chunk of this sub-batch's forward launch
+        aa.cpl = ctx->cpl / team;
         CU(cudaEventRecord(e0, ctx->stream));
         {   // equality words of all periods in dynamic shared memory: 6 planes of (longest slice / 32 + 2) words
             int bm = 1;
@@ -559,11 +574,14 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         rr_init_kernel<<<64, 256, 0, ctx->stream>>>(fa.rr_q, rr_cap, sb.count, fa.rr_ctl);
         CU(cudaGetLastError()); S.launches++;
         int rc = NPORE_OK;
-        switch (ctx->cpl) {
-        case 1: rc = launch_forward<1>(ctx, fa, sb.count); break;
-        case 2: rc = launch_forward<2>(ctx, fa, sb.count); break;
-        case 4: rc = launch_forward<4>(ctx, fa, sb.count); break;
-        default: rc = launch_forward<8>(ctx, fa, sb.count); break;
+        switch (ctx->cpl * 10 + team) {
+        case 11: rc = launch_forward<1, 1>(ctx, fa, sb.count); break;
+        case 21: rc = launch_forward<2, 1>(ctx, fa, sb.count); break;
+        case 22: rc = launch_forward<1, 2>(ctx, fa, sb.count); break;
+        case 41: rc = launch_forward<4, 1>(ctx, fa, sb.count); break;
+        case 42: rc = launch_forward<2, 2>(ctx, fa, sb.count); break;
+        case 81: rc = launch_forward<8, 1>(ctx, fa, sb.count); break;
+        default: rc = launch_forward<4, 2>(ctx, fa, sb.count); break;
         }
         if (rc != NPORE_OK) return rc;
         S.launches++;

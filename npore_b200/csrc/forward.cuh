@@ -41,7 +41,8 @@
 #ifndef FWD_WARPS_WIDE
 #define FWD_WARPS_WIDE 6   // wide bands (CPL >= 4): a ring is 16-32 KB per warp
 #endif
-static __host__ __device__ constexpr int fwd_warps(int cpl) { return cpl >= 4 ? FWD_WARPS_WIDE : FWD_WARPS; }
+// warps per CTA of forward_kernel<CPL, T>: T = warps that share one chunk (a "team": the band is split across them)
+static __host__ __device__ constexpr int fwd_warps(int cpl, int t = 1) { return t == 1 ? (cpl >= 4 ? FWD_WARPS_WIDE : FWD_WARPS) : (cpl >= 4 ? 6 * t : 2 * t); }
 
 struct ForwardArgs {
     const ChunkDesc *chunks;
@@ -154,18 +155,30 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 #define FWD_MINB 4      // min resident CTAs of the narrow-band instantiations: caps ptxas at 128 registers (4 CTAs x 4 warps per SM);
                         // with a hint of 1 it takes 164 and only 3 CTAs fit (measured: 29.0 instead of 26.7 ms per C2 step)
 #endif
-template <int CPL>
-__global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL == 4 ? 2 : 1) forward_kernel(const ForwardArgs a)
+// T > 1: a TEAM of T warps shares one chunk -- the band's NC = 32*CPL*T slots are split across the warps (warp w of the team owns slots
+// [w*32*CPL, (w+1)*32*CPL)), the history ring is the team's, the left neighbour of a warp's first cell comes from the previous warp
+// through a double-buffered mailbox, and one named barrier per anti-diagonal orders ring / mailbox writes against the next step's
+// reads.  Used where one chunk per warp is the wrong granularity: launches with fewer chunks than warp slots (latency bound) and
+// bands wider than 128 cells (<4,2> instead of <8,1>: 168 registers and twice the warps instead of 255 registers).  Teams are not
+// time-sliced (every chunk runs to its end).
+template <int CPL, int T>
+__global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, (CPL * T <= 2) ? FWD_MINB : (CPL == 4 && T == 1) ? 2 : 1) forward_kernel(const ForwardArgs a)
 {
-    constexpr int NC = 32 * CPL;
-    constexpr int TBS = CPL;
-    constexpr uint32_t ROWB = NC * 16, RING_BYTES = NC * 128;        // bytes per ring row / per warp
-    constexpr int SH = CPL == 1 ? 27 : CPL == 2 ? 26 : CPL == 4 ? 25 : 24;      // 32 - log2(NC)
+    constexpr int NC = 32 * CPL * T;
+    constexpr int WARPS = fwd_warps(CPL, T), TEAMS = WARPS / T;
+    constexpr uint32_t ROWB = NC * 16, RING_BYTES = NC * 128;        // bytes per ring row / per team
+    constexpr int SH = NC == 32 ? 27 : NC == 64 ? 26 : NC == 128 ? 25 : 24;      // 32 - log2(NC)
     extern __shared__ float smem[];
     __shared__ float s_sub[64];
     __shared__ uint32_t s_m16[8];
+    __shared__ uint4 s_mail[2][T > 1 ? WARPS : 1];      // {MAT, DEL value, match run, row record} of every warp's last cell, by step parity
+    __shared__ int s_pop[T > 1 ? TEAMS : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int t = threadIdx.x; t < 64; t += fwd_warps(CPL) * 32) {
+    const int team = warp / T, wt = warp % T;            // team of this warp, index inside the team
+    auto team_sync = [&]() {
+        if (T > 1) asm volatile("bar.sync %0, %1;" :: "r"(team + 1), "n"(T * 32) : "memory"); else __syncwarp();
+    };
+    for (int t = threadIdx.x; t < 64; t += WARPS * 32) {
         const int sb = t >> 3, rb = t & 7;
         s_sub[t] = (sb < 5 && rb < 5) ? a.sub_tab[sb * 5 + rb] : 0.f;
     }
@@ -176,18 +189,19 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
     {   // the host sizes the dynamic window from the kernel's static size (launch_forward); never run past it
         uint32_t dyn; asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
         const uint32_t front = smem_base - smem_raw;
-        const uint32_t need = front + (uint32_t)fwd_warps(CPL) * RING_BYTES + (front >= (uint32_t)fwd_warps(CPL) * 1024u ? 0u : (uint32_t)fwd_warps(CPL) * 1024u);
+        const uint32_t need = front + (uint32_t)TEAMS * RING_BYTES + (front >= (uint32_t)WARPS * 1024u ? 0u : (uint32_t)WARPS * 1024u);
         if (need > dyn) {
             if (threadIdx.x == 0) atomicExch(a.err, 1);
             return;
         }
     }
-    const uint32_t wbase = smem_base + (uint32_t)warp * RING_BYTES;
+    const uint32_t wbase = smem_base + (uint32_t)team * RING_BYTES;
     // column-record FIFO of the warp (32 records x 32 B, filled by cp.async 16 records ahead of use): in the alignment slack
     // in front of the rings when it is large enough, else behind them (launch_forward sizes the window the same way)
     constexpr uint32_t STAGE_BYTES = 32u * 32u;
-    const bool stage_front = smem_base - smem_raw >= (uint32_t)fwd_warps(CPL) * STAGE_BYTES;
-    const uint32_t stbase = (stage_front ? smem_raw : smem_base + (uint32_t)fwd_warps(CPL) * RING_BYTES) + (uint32_t)warp * STAGE_BYTES;
+    const bool stage_front = smem_base - smem_raw >= (uint32_t)WARPS * STAGE_BYTES;
+    const uint32_t stbase = (stage_front ? smem_raw : smem_base + (uint32_t)TEAMS * RING_BYTES) + (uint32_t)warp * STAGE_BYTES;
+    const uint32_t mailbase = (uint32_t)__cvta_generic_to_shared(&s_mail[0][0]);
     const uint32_t subbase = (uint32_t)__cvta_generic_to_shared(s_sub);
     const uint32_t m16base = (uint32_t)__cvta_generic_to_shared(s_m16);
 
@@ -205,12 +219,12 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
     const uint32_t in_lim = (uint32_t)(2 * r - 2) << SH;        // es <= in_lim  <=>  1 <= b_col <= 2r-1
     uint32_t mypos[CPL];                                         // byte offset of the lane's slots inside a ring row
 #pragma unroll
-    for (int k = 0; k < CPL; k++) mypos[k] = (uint32_t)(k * 32 + lane) * 16u;
+    for (int k = 0; k < CPL; k++) mypos[k] = (uint32_t)(k * 32 * T + wt * 32 + lane) * 16u;
 
     for (;;) {
         int idx = 0;
         {   // pop the next runnable chunk (FIFO); wait for a push if the queue is momentarily empty
-            if (lane == 0) {
+            if (lane == 0 && wt == 0) {
                 const int pos = atomicAdd(a.rr_ctl, 1);
                 int *qp = a.rr_q + (pos & a.rr_mask);
                 int v;
@@ -223,13 +237,18 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
                 if (v >= 0) __stcg(qp, -1);
                 idx = v;
             }
-            idx = __shfl_sync(NP_FULL, idx, 0);
+            if (T > 1) {      // the team's first warp popped: hand the index to the others
+                if (lane == 0 && wt == 0) s_pop[team] = idx;
+                team_sync();
+                idx = s_pop[team];
+                team_sync();
+            } else idx = __shfl_sync(NP_FULL, idx, 0);
             if (idx < 0) break;
         }
         const int cid = a.order[idx];
         const ChunkDesc c = a.chunks[cid];
         if (!c.valid) {
-            if (lane == 0) { a.out[cid].score = 0.f; atomicAdd(a.rr_ctl + 2, 1); }
+            if (lane == 0 && wt == 0) { a.out[cid].score = 0.f; atomicAdd(a.rr_ctl + 2, 1); }
             continue;
         }
         const ChunkSlot sl = a.slots[idx];
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
         const uint32_t *__restrict__ row = a.rowrec + sl.row_off;
         const uint8_t *__restrict__ refs = a.ref_codes + I.ref_start + min(c.c0, I.ref_len);
         const uint8_t *__restrict__ seqs = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
-        uint16_t *tbp = a.tb + (size_t)sl.tb_off * (32 * TBS) + lane * TBS;
+        uint16_t *tbp = a.tb + (size_t)sl.tb_off * NC + (wt * 32 + lane) * CPL;
         const int B = c.B, imax = c.imax, jmax = c.jmax;
 
         // ---- per-slot state.  At d = 0: jlo = -r, slot s holds column j = -r + ((s + r) mod NC), row i = -j.
@@ -249,7 +268,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
         uint4 ca[CPL], cb[CPL];                           // column record: ca = {S0.A, S0.B, S0.C, S1.A}, cb = {S1.B, S1.C, Z, LEN}
         uint32_t rw[CPL], es[CPL];                        // row record; ((b_col - 1) mod NC) << SH
         int d0 = 0, Id = 0, Dd = 0;
-        uint32_t *st = a.rr_state + (size_t)idx * fwd_rr_state_words(CPL);
+        uint32_t *st = a.rr_state + (size_t)idx * fwd_rr_state_words(NC / 32);
         d0 = (int)ld_state(st);
         if (d0 > 0) {     // resume: scalars, per-lane registers, history ring
             Id = (int)ld_state(st + 1); Dd = (int)ld_state(st + 2);
@@ -262,7 +281,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
                 ca[k] = make_uint4(ld_state(q + 192), ld_state(q + 224), ld_state(q + 256), ld_state(q + 288));
                 cb[k] = make_uint4(ld_state(q + 320), ld_state(q + 352), ld_state(q + 384), ld_state(q + 416));
                 rw[k] = ld_state(q + 448);
-                es[k] = (uint32_t)(lane * CPL + k + r - Dd - 1) << SH;
+                es[k] = (uint32_t)((wt * 32 + lane) * CPL + k + r - Dd - 1) << SH;
             }
             const uint4 *rp = reinterpret_cast<const uint4 *>(st + FWD_RR_HDR + (size_t)FWD_RR_WORDS * CPL * 32);
 #pragma unroll
@@ -275,7 +294,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 Mv1[k] = Iv1[k] = Dv1[k] = dgv[k] = 0.f; Mr1[k] = dgr[k] = 0u;
-                const int s = lane * CPL + k;
+                const int s = (wt * 32 + lane) * CPL + k;
                 const int bc = (s + r) & (NC - 1);
                 es[k] = (uint32_t)(bc - 1) << SH;
                 const int j0 = bc - r;
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
             }
             // the ring starts all-INF: sources before the chunk's first anti-diagonal are no candidates (aln.pyx:497-499)
 #pragma unroll
-            for (int t = 0; t < NC / 4; t++)
+            for (int t = wt; t < NC / 4; t += T)
                 asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%2};" :: "r"(wbase + (uint32_t)(t * 32 + lane) * 16u), "r"(FWD_INF_BITS), "r"(0u) : "memory");
         }
         {   // prime the column-record FIFO: records [cn, (cn & ~15) + 32), cn = the next column to enter the band
@@ -298,13 +317,14 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
             }
             cp_async_wait_all();
         }
-        __syncwarp();
+        team_sync();
         float infd = (float)(100 * (d0 > 0 ? d0 - 1 : 0));   // 100*d, exact in fp32 (d < 2^16); advanced at the top of a step
         uint32_t dsh = (uint32_t)d0 * ROWB;                    // d * ROWB (ring row of this anti-diagonal, before masking)
-        uint16_t *rowp = tbp + (size_t)d0 * (32 * TBS);
+        uint16_t *rowp = tbp + (size_t)d0 * NC;
         uint32_t hist = 0;                                     // op history (bit t = op t+1 steps back), checked variant only
-        int dEnd = min(B, d0 + a.rr_slice);
+        int dEnd = T > 1 ? B : min(B, d0 + a.rr_slice);      // teams are not time-sliced
         int d = d0;
+        uint32_t par = 0u;                                      // step parity: which mailbox half this step writes
 
         // ------------------------------------------------------------------------------------------------ one step
         auto step = [&](auto steady_tag, const uint32_t o, const bool first, uint32_t &nrow_buf, int &nrow_i) {
@@ -312,10 +332,15 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
             float lMv[CPL], lDv[CPL]; uint32_t lMr[CPL];
             if (STEADY || !first) {
                 infd += 100.f;
-                const float a0 = __shfl_sync(NP_FULL, Mv1[CPL - 1], src_lane);
-                const float a1 = __shfl_sync(NP_FULL, Dv1[CPL - 1], src_lane);
-                const uint32_t a2 = __shfl_sync(NP_FULL, Mr1[CPL - 1], src_lane);
-                const uint32_t a3 = __shfl_sync(NP_FULL, rw[CPL - 1], src_lane);
+                const float a0s = __shfl_sync(NP_FULL, Mv1[CPL - 1], src_lane);
+                const float a1s = __shfl_sync(NP_FULL, Dv1[CPL - 1], src_lane);
+                const uint32_t a2s = __shfl_sync(NP_FULL, Mr1[CPL - 1], src_lane);
+                uint32_t a3 = __shfl_sync(NP_FULL, rw[CPL - 1], src_lane);
+                float a0 = a0s, a1 = a1s; uint32_t a2 = a2s;
+                if (T > 1 && lane == 0) {      // the left neighbour of the warp's first cell is the previous warp's last cell
+                    const uint4 m = lds128(mailbase + ((par ^ 1u) * (uint32_t)WARPS + (uint32_t)(team * T + (wt + T - 1) % T)) * 16u);
+                    a0 = __uint_as_float(m.x); a1 = __uint_as_float(m.y); a2 = m.z; a3 = m.w;
+                }
 #pragma unroll
                 for (int k = CPL - 1; k >= 0; k--) {
                     lMv[k] = k ? Mv1[k > 0 ? k - 1 : 0] : a0;
@@ -443,7 +468,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
                                 if (!L) continue;
                                 if (!STEADY && bcn <= __popc(h6 & ((1u << n) - 1u))) continue;
                                 const uint32_t sslot = (uint32_t)(j - n) & (uint32_t)(NC - 1);
-                                const uint32_t off = (uint32_t)((-n) & (NP_RING - 1)) * ROWB + ((sslot % CPL) * 32u + sslot / CPL) * 16u + ((byte & 0x80u) ? 0u : 8u);
+                                const uint32_t off = (uint32_t)((-n) & (NP_RING - 1)) * ROWB + ((sslot % CPL) * (uint32_t)(32 * T) + sslot / CPL) * 16u + ((byte & 0x80u) ? 0u : 8u);
                                 const uint32_t A = ((off | (uint32_t)n) << 16) | (uint32_t)((n - 1) * (a.P.max_l + 1) + (int)L);
                                 shr_eval<NC>(A, lds_u_off<0>(m16base + n * 4u), (byte & 0x80u) ? 0u : 0xffff0000u, dsh, wbase, tabS, trows, true, Sv[k], Sb[k], Sr[k]);
                             }
@@ -522,14 +547,18 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
                 for (int k = 0; k < CPL; k += 2)
                     __stcs(reinterpret_cast<unsigned int *>(rowp) + (k >> 1), __byte_perm(pk[k], pk[k + 1 < CPL ? k + 1 : k], 0x7632));
             }
-            __syncwarp();
+            if (T > 1 && lane == 31)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(mailbase + (par * (uint32_t)WARPS + (uint32_t)warp) * 16u),
+                             "r"(__float_as_uint(Mv[CPL - 1])), "r"(__float_as_uint(Dv[CPL - 1])), "r"(Mr1[CPL - 1]), "r"(rw[CPL - 1]) : "memory");
+            team_sync();
+            par ^= 1u;
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 dgv[k] = lMv[k]; dgr[k] = lMr[k];                 // next step's diagonal neighbour = this step's left
                 Mv1[k] = Mv[k]; Iv1[k] = Iv[k]; Dv1[k] = Dv[k];
             }
             dsh += ROWB;
-            rowp += 32 * TBS;
+            rowp += NC;
         };   // step
 
         // ------------------------------------------------------------------------------------------------ block loop
@@ -614,7 +643,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL) * 32, CPL <= 2 ? FWD_MINB : CPL
 #pragma unroll
         for (int k = 0; k < CPL; k++)
             if (es[k] == ((uint32_t)(r - 1) << SH)) a.out[cid].score = Mv1[k];
-        __syncwarp();
-        if (lane == 0) { __threadfence(); atomicAdd(a.rr_ctl + 2, 1); }
+        team_sync();
+        if (lane == 0 && wt == 0) { __threadfence(); atomicAdd(a.rr_ctl + 2, 1); }
     }
 }

@@ -21,7 +21,7 @@ struct TracebackArgs {
     const uint16_t *tb;
     uint8_t *ops;                 // op scratch, item regions at ItemDesc::out_off
     ChunkOut *out;
-    int r, W, cpl, tbs;
+    int r, W, cpl, tbs;           // cpl: cells per lane of the forward instantiation; tbs * 32 = NC = records per anti-diagonal row
 };
 
 // One warp per chunk: the walk itself is a chain of dependent record loads (every lane reads the same record, a
@@ -40,10 +40,10 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
     const uint8_t *__restrict__ seqs = a.seq_codes + I.seq_start + min(c.r0, I.seq_len);
     const uint16_t *__restrict__ tb = a.tb + (size_t)sl.tb_off * (32 * a.tbs);
     uint8_t *region = a.ops + I.out_off + c.brk;
-    const int cap = c.B - 1, ncm = 32 * a.cpl - 1;
+    const int cap = c.B - 1, ncm = 32 * a.tbs - 1;
     int pos = cap, i = c.imax, j = c.jmax, status = 0;
     const size_t rs = (size_t)32 * a.tbs;
-#define TB_REC(dd, jj) ((dd) >= 0 && (dd) < c.B ? (uint32_t)tb[(size_t)(dd) * rs + (((jj) & ncm) / a.cpl) * a.tbs + (((jj) & ncm) % a.cpl)] : 0u)
+#define TB_REC(dd, jj) ((dd) >= 0 && (dd) < c.B ? (uint32_t)tb[(size_t)(dd) * rs + ((jj) & ncm)] : 0u)
     while (i > 0 || j > 0) {
         if (i < 0) { status = 1; break; }
         if (j < 0) { status = 2; break; }
