@@ -162,7 +162,7 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 // bands wider than 128 cells (<4,2> instead of <8,1>: 168 registers and twice the warps instead of 255 registers).  Teams are not
 // time-sliced (every chunk runs to its end).
 template <int CPL, int T>
-__global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, (CPL * T <= 2) ? FWD_MINB : (CPL == 4 && T == 1) ? 2 : 1) forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : (CPL == 4 && T == 1) ? 2 : 1) forward_kernel(const ForwardArgs a)
 {
     constexpr int NC = 32 * CPL * T;
     constexpr int WARPS = fwd_warps(CPL, T), TEAMS = WARPS / T;
