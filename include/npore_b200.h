@@ -62,7 +62,8 @@ typedef struct npore_ctx npore_ctx;
 #define NPORE_ST_COL_NEG       2
 #define NPORE_ST_RUN_ZERO      3
 #define NPORE_ST_BAD_TYPE      4
-#define NPORE_ST_RUN_OVERFLOW  8    /* an n-polymer (LEN/SHR) run reached the 2047-op record field: CIGAR partial  */
+#define NPORE_ST_RUN_OVERFLOW  8    /* n-polymer (LEN/SHR) runs >= 2047 ops are handled by a transparent second pass (wide kernels);
+                                       this status remains only if more than 65,536 such records occur in one batch: CIGAR partial */
 #define NPORE_ST_BAD_CIGAR     16   /* input CIGAR inconsistent with ref_len / seq_len: item skipped, empty output */
 
 /* output selection flags for npore_run / npore_align_batch */

@@ -82,7 +82,7 @@ struct npore_ctx {
     size_t scratch_budget = 0;
     DevBuf d_sub, d_np;
     // batch-resident
-    DevBuf d_nib, d_nib_start;
+    DevBuf d_nib, d_nib_start, d_ovf;
     DevBuf d_items, d_ref, d_seq, d_rle, d_grp, d_bits, d_cum, d_chunks, d_chunk_out, d_scratch_ops, d_ops,
         d_item_len, d_item_status, d_rleA, d_rleB, d_rle_len, d_rle_which, d_ops_off, d_rle_off, d_pack_ops, d_pack_rle, d_order, d_slots, d_counter;
     // per sub-batch scratch
@@ -131,7 +131,7 @@ inline int chunks_of(int total, int max_b_rows)
     return total > 0 ? (total + step - 1) / step : 0;
 }
 
-template <int CPL, int T>
+template <int CPL, int T, bool WIDE>
 int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 {
     constexpr int WARPS = fwd_warps(CPL, T), TEAMS = WARPS / T;
@@ -140,23 +140,23 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
     // exactly; the kernel re-derives it from the real addresses and raises the error flag instead of running past the window.
     constexpr size_t RING = (size_t)NP_RING * 32 * CPL * T * 16;
     cudaFuncAttributes fattr;
-    CU(cudaFuncGetAttributes(&fattr, forward_kernel<CPL, T>));
+    CU(cudaFuncGetAttributes(&fattr, forward_kernel<CPL, T, WIDE>));
     int reserved = 1024;
     cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device);
     const size_t start = (size_t)reserved + fattr.sharedSizeBytes;
     const size_t slack = (RING - start % RING) % RING;
     // + the per-warp column-record FIFOs (1 KB each): inside the slack when it is large enough, else behind the rings
     const size_t smem = (size_t)TEAMS * RING + slack + (slack >= (size_t)WARPS * 1024 ? 0 : (size_t)WARPS * 1024);
-    CU(cudaFuncSetAttribute(forward_kernel<CPL, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(forward_kernel<CPL, T, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL, T>, WARPS * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<CPL, T, WIDE>, WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
     {   // ask for the smallest shared-memory carve-out that holds the resident CTAs: the rest of the 256 KB is L1 for the
         // score-table lookups (the default picked 196 KB where 164 KB is enough, leaving 56 instead of 92 KB of L1)
         const size_t need = (size_t)per_sm * (smem + fattr.sharedSizeBytes + reserved);
         int pct = (int)((need * 100 + 233472 - 1) / 233472);
         if (pct > 100) pct = 100;
-        CU(cudaFuncSetAttribute(forward_kernel<CPL, T>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        CU(cudaFuncSetAttribute(forward_kernel<CPL, T, WIDE>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     ctx->stats.fwd_warps_per_sm = per_sm * WARPS;
     if (getenv("NPORE_DEBUG"))
@@ -164,7 +164,7 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
                 (size_t)fattr.sharedSizeBytes, fattr.numRegs, per_sm, n_sub);
     int grid = std::min((n_sub + TEAMS - 1) / TEAMS, ctx->sm_count * per_sm);
     if (grid < 1) grid = 1;
-    forward_kernel<CPL, T><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);
+    forward_kernel<CPL, T, WIDE><<<grid, WARPS * 32, smem, ctx->stream>>>(fa);
     CU(cudaGetLastError());
     return NPORE_OK;
 }
@@ -292,7 +292,7 @@ void npore_ctx_destroy(npore_ctx *ctx)
     DevBuf *bufs[] = {&ctx->d_sub, &ctx->d_np, &ctx->d_items, &ctx->d_ref, &ctx->d_seq, &ctx->d_rle, &ctx->d_grp, &ctx->d_bits,
                       &ctx->d_cum, &ctx->d_chunks, &ctx->d_chunk_out, &ctx->d_scratch_ops, &ctx->d_ops, &ctx->d_item_len,
                       &ctx->d_item_status, &ctx->d_rleA, &ctx->d_rleB, &ctx->d_rle_len, &ctx->d_rle_which, &ctx->d_ops_off, &ctx->d_rle_off, &ctx->d_pack_ops, &ctx->d_pack_rle, &ctx->d_order, &ctx->d_slots, &ctx->d_counter,
-                      &ctx->d_nib, &ctx->d_nib_start, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
+                      &ctx->d_nib, &ctx->d_nib_start, &ctx->d_ovf, &ctx->d_colrec, &ctx->d_relaid, &ctx->d_rowrec, &ctx->d_raw_ref, &ctx->d_raw_seq, &ctx->d_tb, &ctx->d_rr_q, &ctx->d_rr_ctl, &ctx->d_rr_state};
     for (auto *b : bufs) b->release();
     for (auto &b : ctx->d_cm) b.release();
     ctx->d_chunk_dst.release(); ctx->d_part_cnt.release();
@@ -434,11 +434,24 @@ int npore_upload(npore_ctx *ctx, const npore_batch *b)
     return NPORE_OK;
 }
 
+static int run_pass(npore_ctx *ctx, uint32_t flags, bool wide, int *n_sat);
+
 int npore_run(npore_ctx *ctx, uint32_t flags)
 {
     if (!ctx) return NPORE_ERR_BAD_ARG;
     if (!ctx->uploaded) return fail(ctx, NPORE_ERR_STATE, "npore_run before npore_upload");
     if ((flags & NPORE_OUT_NO_EXPANDED) && !(flags & NPORE_OUT_RLE)) return fail(ctx, NPORE_ERR_BAD_ARG, "NO_EXPANDED needs RLE");
+    int n_sat = 0;
+    int rc = run_pass(ctx, flags, false, &n_sat);
+    // A traceback met an n-polymer (LEN/SHR) run that saturated the 11-bit record field (>= 2047 ops; the reference has no such
+    // limit): the batch is redone with the WIDE forward kernels, which carry runs unsaturated and keep the true run of such records
+    // in an overflow list.  Costs a second pass for that batch only; status 8 remains only if that list overflows (65,536 records).
+    if (rc == NPORE_OK && n_sat > 0) rc = run_pass(ctx, flags, true, &n_sat);
+    return rc;
+}
+
+static int run_pass(npore_ctx *ctx, uint32_t flags, bool wide, int *n_sat)
+{
     CU(cudaSetDevice(ctx->device));
     ctx->ran = false;
     // an error half-way leaves work queued on the stream and events unrecorded: drain it, so that the context is reusable
@@ -513,7 +526,8 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     CU(ctx->d_rr_state.ensure(sizeof(uint32_t) * fwd_rr_state_words(ctx->cpl) * (size_t)max_sub));
     if (nchunks) CU(cudaMemcpyAsync(ctx->d_slots.p, ctx->slots.data(), sizeof(ChunkSlot) * (size_t)nchunks, cudaMemcpyHostToDevice, ctx->stream));
 
-    CU(cudaMemsetAsync(ctx->d_counter.p, 0, 4, ctx->stream));      // forward-kernel error flag
+    CU(cudaMemsetAsync(ctx->d_counter.p, 0, 16, ctx->stream));     // [0] forward-kernel error flag  [1] overflow records  [2] saturated chunks
+    if (wide) CU(ctx->d_ovf.ensure(sizeof(uint4) * 65536));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     // ---- plan
     int max_ops = 1;
@@ -564,6 +578,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         ForwardArgs fa{};
         fa.chunks = aa.chunks; fa.slots = aa.slots; fa.order = aa.order; fa.n = sb.count;
         fa.items = aa.items; fa.bits = ctx->d_bits.as<uint32_t>(); fa.err = ctx->d_counter.as<int>();
+        fa.ovf = wide ? ctx->d_ovf.as<uint4>() : nullptr; fa.ovf_cap = 65536; fa.ovf_cnt = ctx->d_counter.as<int>() + 1;
         fa.ref_codes = aa.ref_codes; fa.seq_codes = aa.seq_codes; fa.colrec = aa.colrec; fa.relaid = aa.relaid; fa.rowrec = aa.rowrec;
         fa.tb = ctx->d_tb.as<uint16_t>(); fa.tab = ctx->d_np.as<float>(); fa.sub_tab = ctx->d_sub.as<float>();
         fa.out = ctx->d_chunk_out.as<ChunkOut>();
@@ -574,14 +589,21 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         rr_init_kernel<<<64, 256, 0, ctx->stream>>>(fa.rr_q, rr_cap, sb.count, fa.rr_ctl);
         CU(cudaGetLastError()); S.launches++;
         int rc = NPORE_OK;
-        switch (ctx->cpl * 10 + team) {
-        case 11: rc = launch_forward<1, 1>(ctx, fa, sb.count); break;
-        case 21: rc = launch_forward<2, 1>(ctx, fa, sb.count); break;
-        case 22: rc = launch_forward<1, 2>(ctx, fa, sb.count); break;
-        case 41: rc = launch_forward<4, 1>(ctx, fa, sb.count); break;
-        case 42: rc = launch_forward<2, 2>(ctx, fa, sb.count); break;
-        case 81: rc = launch_forward<8, 1>(ctx, fa, sb.count); break;
-        default: rc = launch_forward<4, 2>(ctx, fa, sb.count); break;
+        switch ((ctx->cpl * 10 + team) * (wide ? -1 : 1)) {
+        case 11: rc = launch_forward<1, 1, false>(ctx, fa, sb.count); break;
+        case 21: rc = launch_forward<2, 1, false>(ctx, fa, sb.count); break;
+        case 22: rc = launch_forward<1, 2, false>(ctx, fa, sb.count); break;
+        case 41: rc = launch_forward<4, 1, false>(ctx, fa, sb.count); break;
+        case 42: rc = launch_forward<2, 2, false>(ctx, fa, sb.count); break;
+        case 81: rc = launch_forward<8, 1, false>(ctx, fa, sb.count); break;
+        case 82: rc = launch_forward<4, 2, false>(ctx, fa, sb.count); break;
+        // the fallback for a batch in which a traceback met a saturated n-polymer run (forward.cuh: WIDE)
+        case -11: rc = launch_forward<1, 1, true>(ctx, fa, sb.count); break;
+        case -21: rc = launch_forward<2, 1, true>(ctx, fa, sb.count); break;
+        case -22: rc = launch_forward<1, 2, true>(ctx, fa, sb.count); break;
+        case -41: rc = launch_forward<4, 1, true>(ctx, fa, sb.count); break;
+        case -42: rc = launch_forward<2, 2, true>(ctx, fa, sb.count); break;
+        default: rc = launch_forward<4, 2, true>(ctx, fa, sb.count); break;      // (-81 too: the two-warp form carries W > 128)
         }
         if (rc != NPORE_OK) return rc;
         S.launches++;
@@ -592,6 +614,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         ta.bits = fa.bits; ta.cum = ctx->d_cum.as<uint32_t>(); ta.ref_codes = aa.ref_codes; ta.seq_codes = aa.seq_codes;
         ta.tb = fa.tb; ta.ops = ctx->d_scratch_ops.as<uint8_t>(); ta.out = fa.out;
         ta.r = ctx->P.r; ta.W = ctx->P.W; ta.cpl = ctx->cpl; ta.tbs = ctx->tbs;
+        ta.ovf = fa.ovf; ta.ovf_cnt = fa.ovf_cnt; ta.ovf_cap = fa.ovf_cap; ta.n_sat = ctx->d_counter.as<int>() + 2;
         traceback_kernel<<<(sb.count + TB_THREADS / 32 - 1) / (TB_THREADS / 32), TB_THREADS, 0, ctx->stream>>>(ta);
         CU(cudaGetLastError()); S.launches++;
         CU(cudaEventRecord(e3, ctx->stream));
@@ -600,7 +623,7 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
     // ---- finish
     cudaEvent_t e0 = ctx->ev[4], e1 = ctx->ev[5];
     CU(cudaEventRecord(e0, ctx->stream));
-    const size_t small_bytes = (size_t)n * 12 + (size_t)ctx->n_chunks * sizeof(ChunkOut) + 64;      // + the error flag in the last 4 bytes
+    const size_t small_bytes = (size_t)n * 12 + (size_t)ctx->n_chunks * sizeof(ChunkOut) + 64;      // + three counters in the last 16 bytes
     CU(ctx->h_small.ensure(small_bytes));
     if (n) {
         FinishArgs fa{};
@@ -663,12 +686,13 @@ int npore_run(npore_ctx *ctx, uint32_t flags)
         CU(cudaMemcpyAsync(h_rlen, ctx->d_rle_len.p, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         if (ctx->n_chunks) CU(cudaMemcpyAsync(h_co, ctx->d_chunk_out.p, sizeof(ChunkOut) * (size_t)ctx->n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    int *h_err = reinterpret_cast<int *>(static_cast<char *>(ctx->h_small.p) + small_bytes - 4);
-    *h_err = 0;
-    CU(cudaMemcpyAsync(h_err, ctx->d_counter.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int *h_cnt = reinterpret_cast<int *>(static_cast<char *>(ctx->h_small.p) + small_bytes - 16);
+    h_cnt[0] = h_cnt[1] = h_cnt[2] = 0;
+    CU(cudaMemcpyAsync(h_cnt, ctx->d_counter.p, 12, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    if (*h_err) return fail(ctx, NPORE_ERR_CUDA, "forward kernel: shared-memory window smaller than the history rings");
+    if (h_cnt[0]) return fail(ctx, NPORE_ERR_CUDA, "forward kernel: shared-memory window smaller than the history rings");
+    *n_sat = h_cnt[2];
     for (size_t si = 0; si < ctx->subs.size(); si++) {
         float t;
         cudaEventElapsedTime(&t, ctx->sub_ev[4 * si], ctx->sub_ev[4 * si + 1]); ms_ann += t;

@@ -62,6 +62,7 @@ struct ForwardArgs {
     // round-robin time slicing: run queue + per-chunk saved state
     int *rr_q; int rr_mask; int *rr_ctl;      // ctl[0] head, ctl[1] tail, ctl[2] finished chunks
     int *err;                                 // raised if the shared-memory window does not hold the rings (host bug)
+    uint4 *ovf; int ovf_cap; int *ovf_cnt;    // WIDE runs only: {chunk id, anti-diagonal, slot, run} of records whose LEN/SHR run does not fit 11 bits
     uint32_t *rr_state; int rr_slice;
     AlignParams P;
 };
@@ -126,7 +127,7 @@ __device__ __forceinline__ float bitsel_f(uint32_t m, float x, float y) { return
 //             (L_IDX == 0: run 0, value MAT.VAL), {W2,W3} otherwise; its low 3 bits hold n     [15:0] table row (n, L)
 //   B ceil(65536 / n)        C 0 (start) or 0xffff0000 (continue: SHR.RUN << 16 of the source)
 // An empty descriptor addresses the +INF table row.  `ok` is the checked variant's source test (always true when lean).
-template <int NC>
+template <int NC, uint32_t SAT16 = FWD_SAT16>
 __device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uint32_t dsh, uint32_t wbase, const float *__restrict__ tabS, uint32_t trows,
                                          bool ok, float &Sv, float &Sb, uint32_t &Sr)
 {
@@ -134,14 +135,15 @@ __device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uin
     float base; uint32_t w;
     lds_pair(ad, base, w);
     const uint32_t xs = w & C;                                        // SHR.RUN << 16 of the source, 0 at a tract start
-    const uint32_t q = __umulhi(xs, B);                               // trunc(run / n) <= NP_RUN_SAT < NP_TABQ
+    uint32_t q = __umulhi(xs, B);                                     // trunc(run / n) <= NP_RUN_SAT < NP_TABQ
+    if (SAT16 != FWD_SAT16) q = min(q, (uint32_t)(NP_TABQ - 1));      // (WIDE: runs up to 65535; the tables are constant beyond q = 127)
 #if FWD_TAB_PROBE      // timing probe only (results are wrong): every lookup hits one cache line = the bound on what staging the table could buy
     const float cand = base + __ldg(tabS + ((q * trows + (A & 0xffffu)) & 7u));
 #else
     const float cand = base + __ldg(tabS + (q * trows + (A & 0xffffu)));
 #endif
     const bool better = ok && cand < Sv;
-    const uint32_t nr = __viaddmin_u32(xs, A & 0x70000u, FWD_SAT16);
+    const uint32_t nr = __viaddmin_u32(xs, A & 0x70000u, SAT16);
     Sv = better ? cand : Sv; Sb = better ? base : Sb; Sr = better ? nr : Sr;
 }
 
@@ -161,9 +163,13 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 // reads.  Used where one chunk per warp is the wrong granularity: launches with fewer chunks than warp slots (latency bound) and
 // bands wider than 128 cells (<4,2> instead of <8,1>: 168 registers and twice the warps instead of 255 registers).  Teams are not
 // time-sliced (every chunk runs to its end).
-template <int CPL, int T>
+// WIDE: the fallback for items whose traceback met a saturated n-polymer run (status 8 of the normal kernel): runs are carried
+// unsaturated (16 bits, max_b_rows <= 65000), a record whose LEN/SHR run does not fit the 11-bit field stores 2047 and its true run
+// goes to an overflow list the traceback consults.  Same arithmetic otherwise; api.cu re-runs a batch with WIDE only when needed.
+template <int CPL, int T, bool WIDE = false>
 __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : (CPL == 4 && T == 1) ? 2 : 1) forward_kernel(const ForwardArgs a)
 {
+    constexpr uint32_t SAT16 = WIDE ? 0xffff0000u : FWD_SAT16;        // saturation of the carried LEN / SHR runs (<< 16)
     constexpr int NC = 32 * CPL * T;
     constexpr int WARPS = fwd_warps(CPL, T), TEAMS = WARPS / T;
     constexpr uint32_t ROWB = NC * 16, RING_BYTES = NC * 128;        // bytes per ring row / per team
@@ -416,14 +422,14 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
             for (int k = 0; k < CPL; k++) {
                 bool ok = true;
                 if (!STEADY) { const uint32_t n = (ca[k].x >> 16) & 7u; ok = in[k] && bc[k] > (int)((sip >> (4 * n)) & 7u); }
-                shr_eval<NC>(ca[k].x, ca[k].y, ca[k].z, dsh, wbase, tabS, trows, ok, Sv[k], Sb[k], Sr[k]);
+                shr_eval<NC, SAT16>(ca[k].x, ca[k].y, ca[k].z, dsh, wbase, tabS, trows, ok, Sv[k], Sb[k], Sr[k]);
             }
             if (__any_sync(NP_FULL, any1 != 0u)) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
                     bool ok = true;
                     if (!STEADY) { const uint32_t n = (ca[k].w >> 16) & 7u; ok = in[k] && bc[k] > (int)((sip >> (4 * n)) & 7u); }
-                    shr_eval<NC>(ca[k].w, cb[k].x, cb[k].y, dsh, wbase, tabS, trows, ok, Sv[k], Sb[k], Sr[k]);
+                    shr_eval<NC, SAT16>(ca[k].w, cb[k].x, cb[k].y, dsh, wbase, tabS, trows, ok, Sv[k], Sb[k], Sr[k]);
                 }
             }
             // ---- LEN gather (aln.pyx:602-633): single eligible period, 2-bit k-mer unit compare in registers
@@ -445,9 +451,10 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
                             const uint32_t ad = ((dsh - n * ROWB + mypos[k]) & (RING_BYTES - 16u)) | wbase;
                             const float base = lds_f(ad + (start ? 0u : 4u));                       // MAT.VAL or the carried LEN run-start value
                             const uint32_t run0 = start ? 0u : (lds_u_off<12>(ad) & 0xffffu);
-                            const uint32_t q = __umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u));
+                            uint32_t q = __umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u));
+                            if (WIDE) q = min(q, (uint32_t)(NP_TABQ - 1));
                             const float cand = base + __ldg(tabL + (q * trows + ((D >> 3) & 0x3ffu)));
-                            if (ok && cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + n, (uint32_t)NP_RUN_SAT) << 16; Lb[k] = base; }
+                            if (ok && cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + n, SAT16 >> 16) << 16; Lb[k] = base; }
                         }
                     }
                 }
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
                                 const uint32_t sslot = (uint32_t)(j - n) & (uint32_t)(NC - 1);
                                 const uint32_t off = (uint32_t)((-n) & (NP_RING - 1)) * ROWB + ((sslot % CPL) * (uint32_t)(32 * T) + sslot / CPL) * 16u + ((byte & 0x80u) ? 0u : 8u);
                                 const uint32_t A = ((off | (uint32_t)n) << 16) | (uint32_t)((n - 1) * (a.P.max_l + 1) + (int)L);
-                                shr_eval<NC>(A, lds_u_off<0>(m16base + n * 4u), (byte & 0x80u) ? 0u : 0xffff0000u, dsh, wbase, tabS, trows, true, Sv[k], Sb[k], Sr[k]);
+                                shr_eval<NC, SAT16>(A, lds_u_off<0>(m16base + n * 4u), (byte & 0x80u) ? 0u : 0xffff0000u, dsh, wbase, tabS, trows, true, Sv[k], Sb[k], Sr[k]);
                             }
                         }
                         uint32_t lm = (rb.y >> 22) & (rw[k] >> 20) & 0x3fu;   // LEN, every eligible period
@@ -488,9 +495,10 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
                             const uint32_t ad = ((dsh - (uint32_t)n * ROWB + mypos[k]) & (RING_BYTES - 16u)) | wbase;
                             const float base = lds_f(ad + (start ? 0u : 4u));
                             const uint32_t run0 = start ? 0u : (lds_u_off<12>(ad) & 0xffffu);
-                            const uint32_t q = __umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u));
+                            uint32_t q = __umulhi(run0 << 16, lds_u_off<0>(m16base + n * 4u));
+                            if (WIDE) q = min(q, (uint32_t)(NP_TABQ - 1));
                             const float cand = base + __ldg(tabL + (q * trows + (uint32_t)((n - 1) * (a.P.max_l + 1) + L)));
-                            if (cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + (uint32_t)n, (uint32_t)NP_RUN_SAT) << 16; Lb[k] = base; }
+                            if (cand < Lv[k]) { Lv[k] = cand; Lr[k] = min(run0 + (uint32_t)n, SAT16 >> 16) << 16; Lb[k] = base; }
                         }
                     }
                 }
@@ -521,12 +529,19 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
                 }
                 // MAT = the first minimum in the order diag, INS, LEN, DEL, SHR (strict '<' chain of aln.pyx:585-592)
                 const float best = fmin3(fmin3(dg, Iv[k], Lv[k]), Dv[k], Sv[k]);
-                uint32_t p = ((uint32_t)T_SHR << 29) | Sr[k];
+                uint32_t p = ((uint32_t)T_SHR << 29) | (WIDE ? min(Sr[k], FWD_SAT16) : Sr[k]);
                 if (Dv[k] == best) p = (uint32_t)T_DEL << 29;
-                if (Lv[k] == best) p = ((uint32_t)T_LEN << 29) | Lr[k];
+                if (Lv[k] == best) p = ((uint32_t)T_LEN << 29) | (WIDE ? min(Lr[k], FWD_SAT16) : Lr[k]);
                 if (Iv[k] == best) p = (uint32_t)T_INS << 29;
                 if (dg == best) p = pm;
                 if (!in[k]) p = 0u;
+                if (WIDE) {      // a LEN / SHR record whose run does not fit the field: the true run goes to the overflow list
+                    const uint32_t t3 = p >> 29, full = t3 == (uint32_t)T_LEN ? Lr[k] : Sr[k];
+                    if ((t3 == (uint32_t)T_LEN || t3 == (uint32_t)T_SHR) && full >= FWD_SAT16) {
+                        const int e = atomicAdd(a.ovf_cnt, 1);
+                        if (e < a.ovf_cap) a.ovf[e] = make_uint4((uint32_t)cid, dsh / ROWB, (uint32_t)((wt * 32 + lane) * CPL + k), full >> 16);
+                    }
+                }
                 Mr1[k] = dg == best && in[k] ? pm : 0u;                              // match run of this cell (0 unless TYP == MAT)
                 if (iext && in[k]) p |= NP_REC_IE << 16;
                 if (dext && in[k]) p |= NP_REC_DE << 16;

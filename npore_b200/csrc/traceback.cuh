@@ -22,6 +22,8 @@ struct TracebackArgs {
     uint8_t *ops;                 // op scratch, item regions at ItemDesc::out_off
     ChunkOut *out;
     int r, W, cpl, tbs;           // cpl: cells per lane of the forward instantiation; tbs * 32 = NC = records per anti-diagonal row
+    const uint4 *ovf; const int *ovf_cnt; int ovf_cap;    // overflow list of a WIDE forward run (forward.cuh), else null
+    int *n_sat;                   // incremented for every chunk that ends in status 8 (api.cu re-runs the batch WIDE)
 };
 
 // One warp per chunk: the walk itself is a chain of dependent record loads (every lane reads the same record, a
@@ -60,7 +62,20 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
             run = 1;
             uint32_t q = rec; int jj = j;
             while ((q & NP_REC_DE) && jj > 0) { run++; jj--; q = TB_REC(i + jj, jj); }
-        } else if ((typ == T_LEN || typ == T_SHR) && run == NP_RUN_SAT) { status = 8; break; }   // run field overflow
+        } else if ((typ == T_LEN || typ == T_SHR) && run == NP_RUN_SAT) {
+            // run field saturated: a WIDE forward run left the true run in the overflow list ({chunk, anti-diagonal, slot, run})
+            int found = 0;
+            if (a.ovf) {
+                const int cnt = min(*a.ovf_cnt, a.ovf_cap);
+                for (int e = lane; e < cnt && !found; e += 32) {
+                    const uint4 v = a.ovf[e];
+                    if (v.x == (uint32_t)cid && v.y == (uint32_t)d && v.z == (uint32_t)(j & ncm)) found = (int)v.w;
+                }
+                for (int o = 16; o; o >>= 1) found = max(found, __shfl_xor_sync(NP_FULL, found, o));
+            }
+            if (!found) { status = 8; break; }
+            run = found;
+        }
         if (run < 1) { status = 3; break; }
         if (typ == T_INS || typ == T_LEN || typ == T_DEL || typ == T_SHR) {
             const uint8_t ch = (typ == T_INS || typ == T_LEN) ? 'I' : 'D';
@@ -83,5 +98,6 @@ __global__ void __launch_bounds__(TB_THREADS) traceback_kernel(const TracebackAr
         o.score = a.out[cid].score;
         o.status = status; o.start = c.brk + pos; o.len = cap - pos;
         a.out[cid] = o;
+        if (status == 8 && a.n_sat) atomicAdd(a.n_sat, 1);
     }
 }

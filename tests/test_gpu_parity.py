@@ -169,6 +169,29 @@ def test_long_indel_runs(tables, engine_factory):
     _check(engine_factory(), cases, _oracle_all(cases, S, NP))
 
 
+def test_npolymer_runs_beyond_the_record_field(tables, engine_factory):
+    """LEN / SHR runs of thousands of ops (whole copies of an adjacent tract's unit inserted / deleted): the 11-bit RUN field of
+    the traceback record saturates at 2047, the batch is transparently redone with the WIDE kernels (overflow list), and the
+    result is the reference's -- status 0, no partial CIGAR (round 1 reported status 8 here)."""
+    S, NP = tables
+    rng = np.random.default_rng(8)
+    a = synth.make_reference(300, rng, 0.0, "CGT"); b = synth.make_reference(300, rng, 0.0, "CGT")
+    cases = []
+    for unit, copies, extra in (("A", 12, 3000), ("AC", 9, 1200), ("A", 20, 2047), ("ACG", 8, 900)):
+        tract = unit * copies
+        ref = a + tract + b
+        # insertion of `extra` more copies right after the tract (LEN), and the mirror image (SHR: the read lacks them)
+        cases.append((ref, a + tract + unit * extra + b, "=" * (len(a) + len(tract)) + "I" * (len(unit) * extra) + "=" * len(b)))
+        cases.append((a + tract + unit * extra + b, ref, "=" * (len(a) + len(tract)) + "D" * (len(unit) * extra) + "=" * len(b)))
+    cases.append((a + b, a + b, "=" * 600))                       # an ordinary item in the same batch
+    want = _oracle_all(cases, S, NP)
+    long_runs = [w[0] for w in want if "I" * 2047 in w[0] or "D" * 2047 in w[0]]
+    assert len(long_runs) >= 4
+    _check(engine_factory(), cases, want)
+    small = engine_factory(max_b_rows=1500)                       # several chunks per item: runs cannot span a chunk border
+    _check(small, cases, _oracle_all(cases, S, NP, max_b_rows=1500))
+
+
 def test_bad_cigar_is_reported_not_ub(tables, engine_factory):
     eng = engine_factory()
     ok = ("ACGTACGT", "ACGTACGT", "8=")
