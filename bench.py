@@ -355,7 +355,7 @@ def run_c2(args, config, S, NP, local):
     packed = PackedBatch.from_flat_shared(bases_to_int(ref), np.array([r[3] for r in reads], np.int64), np.array([r[6] - r[3] for r in reads], np.int32),
                                           seq_codes, seq_len, words, off)
     for name in ("ref_codes", "seq_codes", "cigar_rle"):          # pinned staging
-        tt = torch.from_numpy(np.ascontiguousarray(getattr(packed, name))).pin_memory()
+        tt = torch.from_numpy(np.array(getattr(packed, name))).pin_memory()
         setattr(packed, "_pin_" + name, tt)
         setattr(packed, name, tt.numpy())
     eng = Realigner(S, NP, device=local)
@@ -470,7 +470,7 @@ def run_c3(args, config, S, NP, rank, world, local):
     for p in packs:     # pinned staging, as a caller streaming a BAM would hold it
         for name in ("ref_codes", "seq_codes", "cigar_rle"):
             a = getattr(p, name)
-            tt = torch.from_numpy(a).pin_memory()
+            tt = torch.from_numpy(np.array(a)).pin_memory()
             setattr(p, "_pin_" + name, tt)
             setattr(p, name, tt.numpy())
     h2d = sum(p.h2d_bytes() for p in packs)

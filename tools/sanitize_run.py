@@ -9,9 +9,13 @@ from npore_b200.engine import Realigner
 t = np.load(os.path.join(ROOT, "tests/golden/tables.npz")); S, NP = t["sub_scores"], t["np_scores"]
 fz = json.load(gzip.open(os.path.join(ROOT, "tests/golden/fuzz.json.gz"), "rt"))
 bad = 0
-for (r, mb) in [(30, 200), (10, 37), (30, 20000)]:
+# (r, max_b_rows, NPORE_TEAM): few chunks pick the two-warp team kernels by themselves; "1" forces one chunk per warp
+for (r, mb, team) in [(30, 200, "1"), (30, 200, None), (10, 37, None), (30, 20000, "1"), (30, 20000, None)]:
     cases = [c for c in fz if c["r"] == r and c["max_b_rows"] == mb][:8]
     os.environ["NPORE_RR_SLICE"] = "40"
+    os.environ.pop("NPORE_TEAM", None)
+    if team:
+        os.environ["NPORE_TEAM"] = team
     eng = Realigner(S, NP, max_b_rows=mb, r=r)
     refs = [oracle.bases_to_int(c["ref"]) for c in cases]; seqs = [oracle.bases_to_int(c["seq"]) for c in cases]
     outs, scores, status = eng.align_many(refs, seqs, [c["cigar"] for c in cases])
@@ -19,13 +23,34 @@ for (r, mb) in [(30, 200), (10, 37), (30, 20000)]:
     bad += sum(o != c["out"] or s != c["std"] for o, s, c in zip(outs, std, cases))
     eng.get_np_info(refs[0])
     eng.close()
-# a long item (several finish parts), expanded + run-length outputs, wide band (6-warp CTAs)
+os.environ.pop("NPORE_TEAM", None)
+# an SHR run beyond the 11-bit record field: second pass with the WIDE kernels + overflow list; packed (4-bit) read upload
+from npore_b200.engine import PackedBatch, cigars_to_rle_batch
+rng0 = np.random.default_rng(8)
+a_, b_ = synth.make_reference(120, rng0, 0.0, "CGT"), synth.make_reference(120, rng0, 0.0, "CGT")
+refl, seql = a_ + "A" * 12 + "A" * 2300 + b_, a_ + "A" * 12 + b_
+cgl = "=" * 132 + "D" * 2300 + "=" * 120
+eng = Realigner(S, NP)
+o, _, st = eng.align_many([oracle.bases_to_int(refl)], [oracle.bases_to_int(seql)], [cgl])
+bad += (o[0] != oracle.align(oracle.bases_to_int(refl), oracle.bases_to_int(seql), cgl, S, NP)) + int(st[0] != 0)
+nib = np.zeros((len(seql) + 2) // 2 + 1, np.uint8)
+codes16 = np.array([{"A": 1, "C": 2, "G": 4, "T": 8}[c] for c in seql], np.uint8)
+for t, v in enumerate(codes16):          # the read starts at nibble 1 (an odd soft clip)
+    k = t + 1
+    nib[k >> 1] |= (v << 4) if k % 2 == 0 else v
+words, off = cigars_to_rle_batch([cgl])
+pk = PackedBatch.from_flat_shared_nib(oracle.bases_to_int(refl), np.zeros(1, np.int64), np.array([len(refl)], np.int32), nib, np.ones(1, np.int64),
+                                      np.array([len(seql)], np.int32), words, off)
+res = eng.align_packed(pk, 0, eng.new_result(pk, 0, pinned=False))
+bad += res.ops_str(0) != o[0]
+eng.close()
+# a long item (several finish parts), expanded + run-length outputs, wide band (6-warp CTAs; r = 100: two-warp teams of <4,2>)
 rng = np.random.default_rng(3)
 cm = synth.call_length_model(NP)
 ref, tr = synth.make_reference_with_tracts(60_000, rng)
 rd = synth.make_reads(ref, 1, 45_000, rng, cm, tracts=tr)[0]
 from npore_b200 import cig
-for r, mb in ((30, 20000), (60, 5000)):
+for r, mb in ((30, 20000), (60, 5000), (100, 20000)):
     os.environ["NPORE_STD_LONG_MIN"] = "8" if r == 30 else "100000"      # segment-parallel standardisation on the first pass
     eng = Realigner(S, NP, max_b_rows=mb, r=r)
     ir, iq = oracle.bases_to_int(rd[9]), oracle.bases_to_int(rd[7])
