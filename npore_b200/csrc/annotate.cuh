@@ -221,7 +221,9 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
         const int NC = a.nc, CPL = a.cpl, PER = NC / CPL;      // slot s sits at ring position (s % CPL) * PER + s / CPL (forward.cuh)
         for (int j = threadIdx.x; j < sl.col_cap; j += ANN_THREADS) {
             uint2 v = make_uint2(0u, 0u);
-            const uint32_t empty = (uint32_t)a.inf_row;       // "no candidate": the all-INF table row; the source it reads is irrelevant
+            // "no candidate": the all-INF table row; the source pair it reads is irrelevant, but it must be one nobody writes during the
+            // step -- position 0 of the PREVIOUS anti-diagonal's ring row (a read of the current row would race with its owner's store)
+            const uint32_t empty = (((uint32_t)(NP_RING - 1) * (uint32_t)(NC * 16)) << 16) | (uint32_t)a.inf_row;
             uint32_t sA[2] = {empty, empty}, sB[2] = {0u, 0u}, sC[2] = {0u, 0u}, z = 0u, lenw = 0u;
             if (j < len + 8) {
                 uint32_t lenm = 0, nshr = 0, nlen = 0;

@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
     const float *__restrict__ tabS = a.tab;
     const float *__restrict__ tabL = a.tab + (size_t)(a.P.np_rows + 1) * NP_TABQ;
     const uint32_t trows = (uint32_t)a.P.np_rows + 1u;          // row stride of the q-major score tables
-    const uint32_t empty_A = (uint32_t)a.P.np_rows;             // annotate.cuh: "no candidate" -> the +INF table row
+    const uint32_t empty_A = (((uint32_t)(NP_RING - 1) * ROWB) << 16) | (uint32_t)a.P.np_rows;      // annotate.cuh: "no candidate" -> the +INF table row
     const int src_lane = (lane + 31) & 31;
     const int spare = NC - (2 * r + 1);
     // aliasing windows (header): none possible when spare >= 4 or max_n < spare + 3; a run of 6 equal ops when spare == 3 and
