@@ -188,6 +188,12 @@ __device__ __forceinline__ uint32_t raw_byte(const uint8_t *raw, int len, int p,
 {
     return (p >= 0 && p < len) ? (uint32_t)raw[(size_t)p * 8 + n - 1] : 0u;
 }
+// the 8 bytes (periods 1..6) of one position in one load; byte n-1 of the pair = raw[p][n]
+__device__ __forceinline__ uint2 raw_row(const uint8_t *raw, int len, int p)
+{
+    return (p >= 0 && p < len) ? reinterpret_cast<const uint2 *>(raw)[p] : make_uint2(0u, 0u);
+}
+__device__ __forceinline__ uint32_t row_byte(const uint2 v, int n) { return ((n <= 4 ? v.x >> (8 * (n - 1)) : v.y >> (8 * (n - 5))) & 0xffu); }
 
 __device__ __forceinline__ uint32_t kmer2_of(const uint8_t *s, int len, int p, uint32_t &hasN)
 {
@@ -227,9 +233,12 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
             uint32_t sA[2] = {empty, empty}, sB[2] = {0u, 0u}, sC[2] = {0u, 0u}, z = 0u, lenw = 0u;
             if (j < len + 8) {
                 uint32_t lenm = 0, nshr = 0, nlen = 0;
+                uint2 rows[NP_MAXN + 1];
+#pragma unroll
+                for (int t = 0; t <= NP_MAXN; t++) rows[t] = raw_row(raw, len, j - t);
 #pragma unroll
                 for (int n = NP_MAXN; n >= 1; n--) {
-                    const uint32_t b = raw_byte(raw, len, j - n, n);
+                    const uint32_t b = row_byte(rows[n], n);
                     if (n <= 4) v.x |= b << (8 * (n - 1)); else v.y |= b << (8 * (n - 5));
                     const uint32_t L = b & 0x7fu;
                     if (L) {
@@ -243,7 +252,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                         }
                         nshr++;
                     }
-                    const uint32_t o = raw_byte(raw, len, j, n);
+                    const uint32_t o = row_byte(rows[0], n);
                     if ((o & 0x7fu) && (o & 0x80u)) {
                         lenm |= 1u << (n - 1);
                         const uint32_t Lo = o & 0x7fu;
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
             if (i < len + 8) {
 #pragma unroll
                 for (int n = 1; n <= NP_MAXN; n++) {
-                    const uint32_t b = raw_byte(raw, len, i - n, n);
+                    const uint32_t b = row_byte(raw_row(raw, len, i - n), n);
                     if (b & 0x7fu) v |= 1u << (19 + n);
                     if (b & 0x80u) v |= 1u << (25 + n);
                 }
