@@ -144,3 +144,35 @@ def test_pull_model_matches_oracle(tables):
             L.pm_np_raw(ir, len(ir), 6, 100, raw, xs)
             info = oracle.get_np_info(ir)
             assert np.array_equal(raw[:, :6] & 0x7f, info[:, 0, :]) and np.array_equal(xs[:, :6], info[:, 1, :])
+
+
+def test_pull_model_v2_inf_ring_matches_oracle(tables):
+    """oracle/pull_model.c:pm2_align -- the round-2 dataflow of csrc/forward.cuh (INF ring with physical slots, no source tests
+    outside aliasing windows, 16-bit reciprocal, re-laid tables) -- against the scatter-form oracle, incl. band widths with 1-3
+    spare slots and 6-12-base INDEL runs; the explicit-checks form (form 1) must agree too."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("pm2_fuzz", os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "..", "tools", "pm2_fuzz.py"))
+    pm2_fuzz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pm2_fuzz)
+    L = pm2_fuzz.load()
+    S, NP = tables
+    cm = synth.call_length_model(NP)
+    rng = np.random.default_rng(2026)
+    risky = 0
+    for k in range(160):
+        rf, sq, cg, r, mb = synth.fuzz_case(rng, cm)
+        if k % 2:
+            r = int(rng.choice([13, 14, 15, 29, 30, 31, 62, 63]))
+        if k % 3 == 0:                                   # a long insertion into the input path (six equal ops in a row and more)
+            pos = int(rng.integers(0, len(cg) + 1))
+            ins = "".join(rng.choice(list("ACGT"), size=int(rng.integers(6, 12))))
+            ro = sum(1 for c in cg[:pos] if c != "D")
+            sq, cg = sq[:ro] + ins + sq[ro:], cg[:pos] + "I" * len(ins) + cg[pos:]
+        ir, iq = oracle.bases_to_int(rf), oracle.bases_to_int(sq)
+        want, wsc, wst = oracle.align(ir, iq, cg, S, NP, max_b_rows=mb, r=r, return_scores=True)
+        for form in (0, 1):
+            got, gsc, gst, nr = pm2_fuzz.pm2(L, ir, iq, cg, S, NP, mb, r, form)
+            risky += nr
+            assert got == want and gst == wst and np.array_equal(gsc, wsc), f"case {k} form {form} r={r} max_b_rows={mb}"
+    assert risky > 0                                     # the checked path was exercised
