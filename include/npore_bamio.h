@@ -44,6 +44,9 @@ void     npore_bam_close(npore_bam *b);
 int64_t  npore_bam_header_text(const npore_bam *b, const char **text);          /* returns the text length */
 int32_t  npore_bam_n_refs(const npore_bam *b);
 int      npore_bam_ref(const npore_bam *b, int32_t i, const char **name, int64_t *length);
+/* optional: inflate and index the window after the current one on a background thread (the current window stays valid for
+ * npore_bam_columns / npore_bam_gather); the next npore_bam_advance then only swaps it in.  max_bytes as for npore_bam_advance. */
+int      npore_bam_prefetch(npore_bam *b, int64_t max_bytes);
 int64_t  npore_bam_n_records(const npore_bam *b);
 
 /* one value per record of the current window, file order.  end = pos + reference span of the CIGAR (M D N = X); aln_len = SEQ length without

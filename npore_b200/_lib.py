@@ -50,7 +50,7 @@ class PileupBatch(C.Structure):
 EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_set_stream", "npore_count_chunks", "npore_upload", "npore_run", "npore_download",
            "npore_align_batch", "npore_get_np_info", "npore_get_np_info_batch", "npore_confusion_batch", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
 
-IO_EXPORTS = ["npore_io_last_error", "npore_bam_open", "npore_bam_advance", "npore_bam_close", "npore_bam_header_text", "npore_bam_n_refs", "npore_bam_ref",
+IO_EXPORTS = ["npore_io_last_error", "npore_bam_open", "npore_bam_advance", "npore_bam_prefetch", "npore_bam_close", "npore_bam_header_text", "npore_bam_n_refs", "npore_bam_ref",
               "npore_bam_n_records", "npore_bam_columns", "npore_bam_gather", "npore_bam_gather_nib", "npore_sam_bound", "npore_sam_format"]
 
 _lib = None
@@ -99,6 +99,7 @@ def lib():
         L.npore_bam_n_records.argtypes = [vp]
         L.npore_bam_n_records.restype = C.c_int64
         L.npore_bam_columns.argtypes = [vp] * 11
+        L.npore_bam_prefetch.argtypes = [vp, C.c_int64]
         L.npore_bam_gather.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
         L.npore_bam_gather_nib.argtypes = [vp, C.c_int64, vp, C.c_int, vp, vp, vp]
         L.npore_sam_bound.argtypes = [C.c_int64, vp, vp, vp, C.c_int64]

@@ -196,6 +196,8 @@ class NativeBam:
         self._L.npore_bam_columns(self._h, *[cols[k].ctypes.data for k in self.COLUMNS])
         for k, v in cols.items():
             setattr(self, k, v[:n])
+        if n and self.window_bytes:          # streaming: the next window inflates in the background while this one is gathered
+            self._L.npore_bam_prefetch(self._h, self.window_bytes)
         return n
 
     def close(self):
@@ -219,7 +221,18 @@ class NativeBam:
             raise RuntimeError(self._L.npore_io_last_error().decode())
         return nib[:int(boff[-1])], start[:len(sel)]
 
-    def gather(self, sel, n_threads=0, want_qual=True, want_names=True, want_codes=True):
+    def gather_cigar(self, sel, n_threads=0):
+        """Only the CIGAR words of the selected records (S / H dropped): (words uint32, offsets int64[n+1])."""
+        sel = np.ascontiguousarray(sel, dtype=np.int64)
+        off = np.concatenate(([0], np.cumsum(self.n_cigar[sel], dtype=np.int64)))
+        cig = np.empty(max(int(off[-1]), 1), np.uint32)
+        rc = self._L.npore_bam_gather(self._h, len(sel), sel.ctypes.data if len(sel) else None, n_threads, None, None, None, None,
+                                      cig.ctypes.data, off.ctypes.data, None, None)
+        if rc:
+            raise RuntimeError(self._L.npore_io_last_error().decode())
+        return cig[:int(off[-1])], off
+
+    def gather(self, sel, n_threads=0, want_qual=True, want_names=True, want_codes=True, want_cigar=True):
         """Flat arrays of the selected records: dict with seq_ascii, seq_codes, qual_ascii, seq_off, cigar, cig_off, names,
         name_off (soft clips removed, S/H dropped from the CIGAR; bam.pyx:41-44, 59)."""
         sel = np.ascontiguousarray(sel, dtype=np.int64)
@@ -228,7 +241,7 @@ class NativeBam:
         o["seq_ascii"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8)
         o["seq_codes"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8) if want_codes else None
         o["qual_ascii"] = np.empty(max(int(o["seq_off"][-1]), 1), np.uint8) if want_qual else None
-        o["cigar"] = np.empty(max(int(o["cig_off"][-1]), 1), np.uint32)
+        o["cigar"] = np.empty(max(int(o["cig_off"][-1]), 1), np.uint32) if want_cigar else None
         o["names"] = np.empty(max(int(o["name_off"][-1]), 1), np.uint8) if want_names else None
         ptr = lambda a: None if a is None else a.ctypes.data   # noqa: E731
         rc = self._L.npore_bam_gather(self._h, len(sel), ptr(sel) if len(sel) else None, n_threads, ptr(o["seq_ascii"]), ptr(o["seq_codes"]),
@@ -356,12 +369,14 @@ def _realign_segments(bam, segments, fa, codes, codes_lock, pipe, fh, tm, n_thre
                 stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
                 part = sel[cut:stop]
                 t1 = time.perf_counter()
-                g = bam.gather(part, n_threads, want_codes=False)            # ASCII bases / qualities / names for the SAM text
-                nib, nib_start = bam.gather_nib(part, n_threads)              # the upload: BAM's own 4-bit bases
+                nib, nib_start = bam.gather_nib(part, n_threads)              # the upload: BAM's own 4-bit bases + CIGAR words
+                cig_words, cig_off = bam.gather_cigar(part, n_threads)
                 lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
                 packed = PackedBatch.from_flat_shared_nib(cc[lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
-                                                          nib, nib_start, bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
-                item = (pipe.submit(packed, flags), take_columns(bam, part), g, len(part))
+                                                          nib, nib_start, bam.aln_len[part], cig_words, cig_off)
+                fut = pipe.submit(packed, flags)                              # the GPU starts; the SAM-text gather runs beside it
+                g = bam.gather(part, n_threads, want_codes=False, want_cigar=False)      # ASCII bases / qualities / names
+                item = (fut, take_columns(bam, part), g, len(part))
                 tm["gather"] += time.perf_counter() - t1
                 pending.put(item)
                 cut = stop
@@ -552,12 +567,14 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
                     stop = max(cut + 1, int(np.searchsorted(ops, (ops[cut - 1] if cut else 0) + max_batch_ops, "right")))
                     part = sel[cut:stop]
                     t1 = time.perf_counter()
-                    g = bam.gather(part, n_threads, want_codes=False)        # ASCII bases / qualities / names for the SAM text
-                    nib, nib_start = bam.gather_nib(part, n_threads)          # the upload: BAM's own 4-bit bases
+                    nib, nib_start = bam.gather_nib(part, n_threads)          # the upload: BAM's own 4-bit bases + CIGAR words
+                    cig_words, cig_off = bam.gather_cigar(part, n_threads)
                     lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
                     packed = PackedBatch.from_flat_shared_nib(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
-                                                              nib, nib_start, bam.aln_len[part], g["cigar"][:int(g["cig_off"][-1])], g["cig_off"])
-                    item = (pipe.submit(packed, flags), take_columns(bam, part), g, len(part))
+                                                              nib, nib_start, bam.aln_len[part], cig_words, cig_off)
+                    fut = pipe.submit(packed, flags)                          # the GPU starts; the SAM-text gather runs beside it
+                    g = bam.gather(part, n_threads, want_codes=False, want_cigar=False)  # ASCII bases / qualities / names
+                    item = (fut, take_columns(bam, part), g, len(part))
                     tm["gather"] += time.perf_counter() - t1
                     pending.put(item)                                        # blocks while n_inflight + 1 batches are unfinished
                     cut = stop

@@ -53,7 +53,10 @@ struct npore_bam {
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
     std::vector<Rec> recs;                // records of the current window
-    ~npore_bam() { if (fh) std::fclose(fh); }
+    // the NEXT window, inflated and indexed by a background thread while the caller gathers from the current one (npore_bam_prefetch)
+    std::vector<uint8_t> ndata; size_t nhead = 0; std::vector<Rec> nrecs;
+    std::thread pf; int64_t pf_rc = 0; std::string pf_err;
+    ~npore_bam() { if (pf.joinable()) pf.join(); if (fh) std::fclose(fh); }
 };
 
 namespace {
@@ -93,13 +96,13 @@ const char *npore_io_last_error(void) { return g_err.c_str(); }
 
 // Append the next BGZF members of the file to b->data until at least `want` more inflated bytes are there (or EOF).
 // Member layout: 12 fixed bytes, XLEN extra (subfield 'B','C' holds BSIZE = member size - 1), deflate data, CRC32, ISIZE.
-static int load_blocks(npore_bam *b, size_t want)
+static int load_blocks(npore_bam *b, std::vector<uint8_t> &data, size_t want)
 {
     struct Blk { size_t coff, clen, uoff, ulen; uint32_t crc; };
     std::vector<uint8_t> cbuf;
     std::vector<Blk> blks;
     size_t added = 0;
-    const size_t base = b->data.size();
+    const size_t base = data.size();
     while (!b->eof && added < want) {
         uint8_t hd[12];
         const size_t got = std::fread(hd, 1, 12, b->fh);
@@ -126,7 +129,7 @@ static int load_blocks(npore_bam *b, size_t want)
         added += k.ulen;
         blks.push_back(k);
     }
-    b->data.resize(base + added);
+    data.resize(base + added);
     std::atomic<int> bad{0};
     parallel_for((int64_t)blks.size(), b->n_threads, [&](int64_t lo, int64_t hi) {
         z_stream zs;
@@ -136,10 +139,10 @@ static int load_blocks(npore_bam *b, size_t want)
             std::memset(&zs, 0, sizeof(zs));
             if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
             zs.next_in = const_cast<Bytef *>(&cbuf[m.coff]); zs.avail_in = (uInt)m.clen;
-            zs.next_out = &b->data[m.uoff]; zs.avail_out = (uInt)m.ulen;
+            zs.next_out = &data[m.uoff]; zs.avail_out = (uInt)m.ulen;
             const int rc = inflate(&zs, Z_FINISH);
             inflateEnd(&zs);
-            if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), &b->data[m.uoff], (uInt)m.ulen) != m.crc) { bad = 1; return; }
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), &data[m.uoff], (uInt)m.ulen) != m.crc) { bad = 1; return; }
         }
     });
     if (bad) return io_fail(NPORE_IO_ERR_FORMAT, "BGZF member failed to inflate (corrupt data or CRC mismatch)");
@@ -158,7 +161,7 @@ int npore_bam_open(const char *path, int n_threads, npore_bam **out)
     auto have = [&](size_t n) -> int {        // 1: n bytes available, 0: file ended first, <0: error
         while (bam->data.size() < n) {
             if (bam->eof) return 0;
-            const int rc = load_blocks(bam, std::max<size_t>(n - bam->data.size(), 1));
+            const int rc = load_blocks(bam, bam->data, std::max<size_t>(n - bam->data.size(), 1));
             if (rc) return rc;
         }
         return 1;
@@ -188,39 +191,36 @@ int npore_bam_open(const char *path, int n_threads, npore_bam **out)
 
 // Next window of records: drops the previous window, inflates members until at least max_bytes of record data are
 // available (<= 0: the rest of the file) and indexes the complete records.  Returns their number; 0 at end of file.
-int64_t npore_bam_advance(npore_bam *bam, int64_t max_bytes)
+static int64_t fill_window(npore_bam *bam, std::vector<uint8_t> &data, std::vector<Rec> &recs, size_t &head, int64_t max_bytes)
 {
-    if (!bam) return io_fail(NPORE_IO_ERR_ARG, "null handle");
-    bam->recs.clear();
-    if (bam->head) { bam->data.erase(bam->data.begin(), bam->data.begin() + (std::ptrdiff_t)bam->head); bam->head = 0; }
     const size_t want = max_bytes > 0 ? (size_t)max_bytes : (size_t)-1;
     std::vector<int64_t> offs;
     size_t at = 0;
     for (;;) {
         // index the complete records present
-        while (at + 4 <= bam->data.size() && !(at >= want && !offs.empty())) {
-            const size_t bs = rd32(&bam->data[at]);
+        while (at + 4 <= data.size() && !(at >= want && !offs.empty())) {
+            const size_t bs = rd32(&data[at]);
             if (bs < 32) return io_fail(NPORE_IO_ERR_FORMAT, "corrupt BAM record (block_size < 32)");
-            if (at + 4 + bs > bam->data.size()) break;
+            if (at + 4 + bs > data.size()) break;
             offs.push_back((int64_t)at + 4);
             at += 4 + bs;
         }
-        if ((at >= want && !offs.empty()) || (bam->eof && (at + 4 > bam->data.size() || at + 4 + rd32(&bam->data[at]) > bam->data.size()))) break;
+        if ((at >= want && !offs.empty()) || (bam->eof && (at + 4 > data.size() || at + 4 + rd32(&data[at]) > data.size()))) break;
         const size_t need = std::max<size_t>(want > at ? std::min<size_t>(want - at, (size_t)1 << 30) : 1, 1);
-        const int rc = load_blocks(bam, need);
+        const int rc = load_blocks(bam, data, need);
         if (rc) return rc;
     }
-    if (bam->eof && offs.empty() && at != bam->data.size())
+    if (bam->eof && offs.empty() && at != data.size())
         return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM record at end of file");
-    bam->head = at;
-    const std::vector<uint8_t> &d = bam->data;
+    head = at;
+    const std::vector<uint8_t> &d = data;
     const int n_threads = bam->n_threads;
-    bam->recs.resize(offs.size());
+    recs.resize(offs.size());
     parallel_for((int64_t)offs.size(), n_threads, [&](int64_t lo, int64_t hi) {
         for (int64_t k = lo; k < hi; k++) {
             const uint8_t *r = &d[(size_t)offs[(size_t)k]];
             const size_t bs = rd32(r - 4);
-            Rec &o = bam->recs[(size_t)k];
+            Rec &o = recs[(size_t)k];
             o.off = offs[(size_t)k];
             o.ref_id = (int32_t)rd32(r); o.pos = (int32_t)rd32(r + 4);
             o.name_len = r[8] ? r[8] - 1 : 0; o.mapq = r[9];
@@ -250,7 +250,36 @@ int64_t npore_bam_advance(npore_bam *bam, int64_t max_bytes)
             o.hp = find_hp(aux, end);
         }
     });
-    return (int64_t)bam->recs.size();
+    return (int64_t)recs.size();
+}
+
+int64_t npore_bam_advance(npore_bam *bam, int64_t max_bytes)
+{
+    if (!bam) return io_fail(NPORE_IO_ERR_ARG, "null handle");
+    if (bam->pf.joinable()) {             // the next window was prefetched: swap it in
+        bam->pf.join();
+        if (bam->pf_rc < 0) return io_fail((int)bam->pf_rc, bam->pf_err);
+        std::swap(bam->data, bam->ndata); std::swap(bam->recs, bam->nrecs); bam->head = bam->nhead;
+        return bam->pf_rc;
+    }
+    bam->recs.clear();
+    if (bam->head) { bam->data.erase(bam->data.begin(), bam->data.begin() + (std::ptrdiff_t)bam->head); bam->head = 0; }
+    return fill_window(bam, bam->data, bam->recs, bam->head, max_bytes);
+}
+
+// Start inflating + indexing the window AFTER the current one on a background thread; the current window stays valid for
+// npore_bam_columns / _gather until the next npore_bam_advance, which then only swaps.  Overlaps BGZF inflate with the caller's gathers.
+int npore_bam_prefetch(npore_bam *bam, int64_t max_bytes)
+{
+    if (!bam) return io_fail(NPORE_IO_ERR_ARG, "null handle");
+    if (bam->pf.joinable()) return NPORE_IO_OK;
+    bam->ndata.assign(bam->data.begin() + (std::ptrdiff_t)bam->head, bam->data.end());      // the bytes carried over (a partial record)
+    bam->nrecs.clear(); bam->nhead = 0; bam->pf_rc = 0;
+    bam->pf = std::thread([bam, max_bytes]() {
+        bam->pf_rc = fill_window(bam, bam->ndata, bam->nrecs, bam->nhead, max_bytes);
+        if (bam->pf_rc < 0) bam->pf_err = g_err;
+    });
+    return NPORE_IO_OK;
 }
 
 void npore_bam_close(npore_bam *b) { delete b; }
