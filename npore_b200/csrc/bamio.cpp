@@ -8,7 +8,9 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,6 +34,34 @@ void parallel_for(int64_t n, int n_threads, F &&body)        // body(begin, end)
     for (auto &th : pool) th.join();
 }
 
+// Byte buffer without value-initialisation (std::vector::resize memsets: 60 MB of zeroing + fresh page faults per file were a third of
+// the serial part of a window load); capacity is kept across windows.
+struct Bytes {
+    uint8_t *p = nullptr; size_t n = 0, cap = 0;
+    Bytes() = default;
+    Bytes(const Bytes &) = delete;
+    Bytes &operator=(const Bytes &) = delete;
+    ~Bytes() { std::free(p); }
+    size_t size() const { return n; }
+    uint8_t *data() { return p; }
+    const uint8_t *data() const { return p; }
+    uint8_t &operator[](size_t i) { return p[i]; }
+    const uint8_t &operator[](size_t i) const { return p[i]; }
+    void resize(size_t m)
+    {
+        if (m > cap) {
+            const size_t c = std::max(m, cap + cap / 2 + 4096);
+            uint8_t *q = (uint8_t *)std::realloc(p, c);
+            if (!q) throw std::bad_alloc();
+            p = q; cap = c;
+        }
+        n = m;
+    }
+    void erase_front(size_t k) { if (k) { std::memmove(p, p + k, n - k); n -= k; } }
+    void assign(const uint8_t *b, const uint8_t *e) { resize((size_t)(e - b)); if (e > b) std::memcpy(p, b, (size_t)(e - b)); }
+    void swap(Bytes &o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
+};
+
 inline uint32_t rd32(const uint8_t *p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
 inline uint16_t rd16(const uint8_t *p) { uint16_t v; std::memcpy(&v, p, 2); return v; }
 
@@ -47,14 +77,14 @@ struct npore_bam {
     FILE *fh = nullptr;
     bool eof = false;
     int n_threads = 0;
-    std::vector<uint8_t> data;            // inflated BAM stream of the current window (starts with the bytes carried over)
+    Bytes data;                           // inflated BAM stream of the current window (starts with the bytes carried over)
     size_t head = 0;                      // first byte of `data` not yet consumed (header / complete records before it)
     std::string text;
     std::vector<std::string> ref_names;
     std::vector<int64_t> ref_lens;
     std::vector<Rec> recs;                // records of the current window
     // the NEXT window, inflated and indexed by a background thread while the caller gathers from the current one (npore_bam_prefetch)
-    std::vector<uint8_t> ndata; size_t nhead = 0; std::vector<Rec> nrecs;
+    Bytes ndata; size_t nhead = 0; std::vector<Rec> nrecs;
     std::thread pf; int64_t pf_rc = 0; std::string pf_err;
     ~npore_bam() { if (pf.joinable()) pf.join(); if (fh) std::fclose(fh); }
 };
@@ -96,10 +126,10 @@ const char *npore_io_last_error(void) { return g_err.c_str(); }
 
 // Append the next BGZF members of the file to b->data until at least `want` more inflated bytes are there (or EOF).
 // Member layout: 12 fixed bytes, XLEN extra (subfield 'B','C' holds BSIZE = member size - 1), deflate data, CRC32, ISIZE.
-static int load_blocks(npore_bam *b, std::vector<uint8_t> &data, size_t want)
+static int load_blocks(npore_bam *b, Bytes &data, size_t want)
 {
     struct Blk { size_t coff, clen, uoff, ulen; uint32_t crc; };
-    std::vector<uint8_t> cbuf;
+    Bytes cbuf;
     std::vector<Blk> blks;
     size_t added = 0;
     const size_t base = data.size();
@@ -131,19 +161,23 @@ static int load_blocks(npore_bam *b, std::vector<uint8_t> &data, size_t want)
     }
     data.resize(base + added);
     std::atomic<int> bad{0};
-    parallel_for((int64_t)blks.size(), b->n_threads, [&](int64_t lo, int64_t hi) {
+    // members are handed out one at a time (an atomic cursor: their inflate cost varies), one z_stream per thread, reset per member
+    std::atomic<int64_t> next{0};
+    const int64_t nblk = (int64_t)blks.size();
+    parallel_for(std::min<int64_t>(nblk, 64), b->n_threads, [&](int64_t, int64_t) {
         z_stream zs;
-        for (int64_t k = lo; k < hi; k++) {
+        std::memset(&zs, 0, sizeof(zs));
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+        for (int64_t k; (k = next.fetch_add(1)) < nblk && !bad;) {
             const Blk &m = blks[(size_t)k];
             if (!m.ulen) continue;
-            std::memset(&zs, 0, sizeof(zs));
-            if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+            inflateReset(&zs);
             zs.next_in = const_cast<Bytef *>(&cbuf[m.coff]); zs.avail_in = (uInt)m.clen;
             zs.next_out = &data[m.uoff]; zs.avail_out = (uInt)m.ulen;
             const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), &data[m.uoff], (uInt)m.ulen) != m.crc) { bad = 1; return; }
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || crc32(crc32(0L, Z_NULL, 0), &data[m.uoff], (uInt)m.ulen) != m.crc) bad = 1;
         }
+        inflateEnd(&zs);
     });
     if (bad) return io_fail(NPORE_IO_ERR_FORMAT, "BGZF member failed to inflate (corrupt data or CRC mismatch)");
     return NPORE_IO_OK;
@@ -157,6 +191,7 @@ int npore_bam_open(const char *path, int n_threads, npore_bam **out)
     if (!fh) return io_fail(NPORE_IO_ERR_OPEN, std::string("cannot open ") + path);
     npore_bam *bam = new npore_bam();
     bam->fh = fh; bam->n_threads = n_threads;
+    std::setvbuf(fh, nullptr, _IOFBF, 1 << 20);          // the member headers are read 12 + 6 bytes at a time
     // ---- BAM header: magic, l_text, text, n_ref, (l_name, name, l_ref)*; members are loaded until it is complete
     auto have = [&](size_t n) -> int {        // 1: n bytes available, 0: file ended first, <0: error
         while (bam->data.size() < n) {
@@ -191,7 +226,7 @@ int npore_bam_open(const char *path, int n_threads, npore_bam **out)
 
 // Next window of records: drops the previous window, inflates members until at least max_bytes of record data are
 // available (<= 0: the rest of the file) and indexes the complete records.  Returns their number; 0 at end of file.
-static int64_t fill_window(npore_bam *bam, std::vector<uint8_t> &data, std::vector<Rec> &recs, size_t &head, int64_t max_bytes)
+static int64_t fill_window(npore_bam *bam, Bytes &data, std::vector<Rec> &recs, size_t &head, int64_t max_bytes)
 {
     const size_t want = max_bytes > 0 ? (size_t)max_bytes : (size_t)-1;
     std::vector<int64_t> offs;
@@ -213,7 +248,7 @@ static int64_t fill_window(npore_bam *bam, std::vector<uint8_t> &data, std::vect
     if (bam->eof && offs.empty() && at != data.size())
         return io_fail(NPORE_IO_ERR_FORMAT, "truncated BAM record at end of file");
     head = at;
-    const std::vector<uint8_t> &d = data;
+    const Bytes &d = data;
     const int n_threads = bam->n_threads;
     recs.resize(offs.size());
     parallel_for((int64_t)offs.size(), n_threads, [&](int64_t lo, int64_t hi) {
@@ -259,11 +294,11 @@ int64_t npore_bam_advance(npore_bam *bam, int64_t max_bytes)
     if (bam->pf.joinable()) {             // the next window was prefetched: swap it in
         bam->pf.join();
         if (bam->pf_rc < 0) return io_fail((int)bam->pf_rc, bam->pf_err);
-        std::swap(bam->data, bam->ndata); std::swap(bam->recs, bam->nrecs); bam->head = bam->nhead;
+        bam->data.swap(bam->ndata); std::swap(bam->recs, bam->nrecs); bam->head = bam->nhead;
         return bam->pf_rc;
     }
     bam->recs.clear();
-    if (bam->head) { bam->data.erase(bam->data.begin(), bam->data.begin() + (std::ptrdiff_t)bam->head); bam->head = 0; }
+    if (bam->head) { bam->data.erase_front(bam->head); bam->head = 0; }
     return fill_window(bam, bam->data, bam->recs, bam->head, max_bytes);
 }
 
@@ -273,7 +308,7 @@ int npore_bam_prefetch(npore_bam *bam, int64_t max_bytes)
 {
     if (!bam) return io_fail(NPORE_IO_ERR_ARG, "null handle");
     if (bam->pf.joinable()) return NPORE_IO_OK;
-    bam->ndata.assign(bam->data.begin() + (std::ptrdiff_t)bam->head, bam->data.end());      // the bytes carried over (a partial record)
+    bam->ndata.assign(bam->data.data() + bam->head, bam->data.data() + bam->data.size());      // the bytes carried over (a partial record)
     bam->nrecs.clear(); bam->nhead = 0; bam->pf_rc = 0;
     bam->pf = std::thread([bam, max_bytes]() {
         bam->pf_rc = fill_window(bam, bam->ndata, bam->nrecs, bam->nhead, max_bytes);
