@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 OPS_PER_CU = 28
 BYTES_PER_CU = 2         # packed (TYP,RUN) traceback record
 # forward_kernel<2> on the C2 batch, one ncu --set full capture (profiles/r02_forward_metrics.txt): dram read + write bytes per launch
-NCU_DRAM_BYTES_PER_LAUNCH = 9.48e9
+NCU_DRAM_BYTES_PER_LAUNCH = 9.494e9
 C3_TILES, TILE_REF, TILE_READS, READ_LEN = 64, 1_000_000, 3000, 10000
 REF_CHUNKSIZE_NOTE = "imap_unordered chunksize = min(100, reads / (4 * cores)) (realign.py:110-114 uses 100; smaller here so that a bounded sample still spreads over all cores)"
 
