@@ -60,6 +60,31 @@ def test_fuzz_golden_reference_outputs(tables, golden, engine_factory):
         _check(eng, [(c["ref"], c["seq"], c["cigar"]) for c in cases], want)
 
 
+@pytest.mark.parametrize("team", ["1", "2"])
+def test_one_warp_and_team_forms_of_the_forward_kernel(tables, golden, monkeypatch, team):
+    """forward_kernel<CPL, T>: one chunk per warp (T = 1) and a two-warp team per chunk (T = 2: band split across the warps, team
+    ring, mailbox, named barrier) forced through NPORE_TEAM -- both must reproduce the reference's outputs (CIGARs, chunk scores,
+    standardised CIGARs) on the golden fuzz vectors and on multi-kb reads at r = 30 / 60 / 100."""
+    from npore_b200.engine import Realigner
+    monkeypatch.setenv("NPORE_TEAM", team)
+    S, NP = tables
+    groups = {}
+    for c in golden("fuzz.json.gz"):
+        groups.setdefault((c["r"], c["max_b_rows"]), []).append(c)
+    for (r, mb), cases in sorted(groups.items()):
+        eng = Realigner(S, NP, max_b_rows=mb, r=r)
+        _check(eng, [(c["ref"], c["seq"], c["cigar"]) for c in cases], [(c["out"], c["scores"], 0, c["std"]) for c in cases])
+        eng.close()
+    rng = np.random.default_rng(90 + int(team))
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(60_000, rng)
+    cases = [(rd[9], rd[7], cig.expand_cigar(rd[5])) for rd in synth.make_reads(ref, 6, 7000, rng, cm, tracts=tr)]
+    for r in (30, 60, 100):
+        eng = Realigner(S, NP, r=r, max_b_rows=3000)
+        _check(eng, cases, _oracle_all(cases, S, NP, r=r, max_b_rows=3000))
+        eng.close()
+
+
 def test_golden_sam_through_realign_reads(tables, golden, tmp_path):
     """bam.realign_reads on test/data/reads.sam + ref.fasta reproduces test/data/npore_realigned.sam, every field."""
     from npore_b200 import bam, cfg
