@@ -278,23 +278,28 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
         d0 = (int)ld_state(st);
         if (d0 > 0) {     // resume: scalars, per-lane registers, history ring
             Id = (int)ld_state(st + 1); Dd = (int)ld_state(st + 2);
-            const uint32_t *sp = st + FWD_RR_HDR + lane;
+            constexpr int LT = 32 * T;                          // lanes of the team: the stride of one saved register word
+            const uint32_t *sp = st + FWD_RR_HDR + wt * 32 + lane;
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
-                const uint32_t *q = sp + (size_t)k * FWD_RR_WORDS * 32;
-                Mv1[k] = __uint_as_float(ld_state(q)); Iv1[k] = __uint_as_float(ld_state(q + 32)); Dv1[k] = __uint_as_float(ld_state(q + 64));
-                dgv[k] = __uint_as_float(ld_state(q + 96)); Mr1[k] = ld_state(q + 128); dgr[k] = ld_state(q + 160);
-                ca[k] = make_uint4(ld_state(q + 192), ld_state(q + 224), ld_state(q + 256), ld_state(q + 288));
-                cb[k] = make_uint4(ld_state(q + 320), ld_state(q + 352), ld_state(q + 384), ld_state(q + 416));
-                rw[k] = ld_state(q + 448);
+                const uint32_t *q = sp + (size_t)k * FWD_RR_WORDS * LT;
+                Mv1[k] = __uint_as_float(ld_state(q)); Iv1[k] = __uint_as_float(ld_state(q + LT)); Dv1[k] = __uint_as_float(ld_state(q + 2 * LT));
+                dgv[k] = __uint_as_float(ld_state(q + 3 * LT)); Mr1[k] = ld_state(q + 4 * LT); dgr[k] = ld_state(q + 5 * LT);
+                ca[k] = make_uint4(ld_state(q + 6 * LT), ld_state(q + 7 * LT), ld_state(q + 8 * LT), ld_state(q + 9 * LT));
+                cb[k] = make_uint4(ld_state(q + 10 * LT), ld_state(q + 11 * LT), ld_state(q + 12 * LT), ld_state(q + 13 * LT));
+                rw[k] = ld_state(q + 14 * LT);
                 es[k] = (uint32_t)((wt * 32 + lane) * CPL + k + r - Dd - 1) << SH;
             }
-            const uint4 *rp = reinterpret_cast<const uint4 *>(st + FWD_RR_HDR + (size_t)FWD_RR_WORDS * CPL * 32);
+            const uint4 *rp = reinterpret_cast<const uint4 *>(st + FWD_RR_HDR + (size_t)FWD_RR_WORDS * CPL * LT);
 #pragma unroll
-            for (int t = 0; t < NC / 4; t++) {
+            for (int t = wt; t < NC / 4; t += T) {
                 const uint4 v = ld_state4(rp + t * 32 + lane);
                 asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(wbase + (uint32_t)(t * 32 + lane) * 16u), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
             }
+            // the mailbox entry the next step reads (par = 0 reads half 1): the warp's last cell as the previous step left it
+            if (T > 1 && lane == 31)
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(mailbase + ((uint32_t)WARPS + (uint32_t)warp) * 16u),
+                             "r"(__float_as_uint(Mv1[CPL - 1])), "r"(__float_as_uint(Dv1[CPL - 1])), "r"(Mr1[CPL - 1]), "r"(rw[CPL - 1]) : "memory");
         } else {
             const uint4 e0 = make_uint4(empty_A, 0u, 0u, empty_A), e1 = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -328,7 +333,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
         uint32_t dsh = (uint32_t)d0 * ROWB;                    // d * ROWB (ring row of this anti-diagonal, before masking)
         uint16_t *rowp = tbp + (size_t)d0 * NC;
         uint32_t hist = 0;                                     // op history (bit t = op t+1 steps back), checked variant only
-        int dEnd = T > 1 ? B : min(B, d0 + a.rr_slice);      // teams are not time-sliced
+        int dEnd = min(B, d0 + a.rr_slice);
         int d = d0;
         uint32_t par = 0u;                                      // step parity: which mailbox half this step writes
 
@@ -583,8 +588,14 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
                 if (dEnd >= B) break;
                 // slice over: hand the chunk back only if another chunk is waiting for a warp (tail - head > 0)
                 int queued = 0;
-                if (lane == 0) queued = ld_cg_poll(a.rr_ctl + 1) - ld_cg_poll(a.rr_ctl);
-                if (__shfl_sync(NP_FULL, queued, 0) > 0) break;
+                if (lane == 0 && wt == 0) queued = ld_cg_poll(a.rr_ctl + 1) - ld_cg_poll(a.rr_ctl);
+                if (T > 1) {      // one decision per team
+                    if (lane == 0 && wt == 0) s_pop[team] = queued;
+                    team_sync();
+                    queued = s_pop[team];
+                    team_sync();
+                } else queued = __shfl_sync(NP_FULL, queued, 0);
+                if (queued > 0) break;
                 dEnd = min(B, dEnd + a.rr_slice);
             }
             uint32_t nrow_buf = row[Id + r + 1 + lane];       // the next 32 rows to enter the band (at b_col == 0)
@@ -628,27 +639,29 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : 
         }
 
         if (dEnd < B) {     // slice over: save the chunk's state and hand it back to the run queue
-            uint32_t *sp = st + FWD_RR_HDR + lane;
+            constexpr int LT = 32 * T;
+            uint32_t *sp = st + FWD_RR_HDR + wt * 32 + lane;
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
-                uint32_t *q = sp + (size_t)k * FWD_RR_WORDS * 32;
-                __stcg(q, __float_as_uint(Mv1[k])); __stcg(q + 32, __float_as_uint(Iv1[k])); __stcg(q + 64, __float_as_uint(Dv1[k]));
-                __stcg(q + 96, __float_as_uint(dgv[k])); __stcg(q + 128, Mr1[k]); __stcg(q + 160, dgr[k]);
-                __stcg(q + 192, ca[k].x); __stcg(q + 224, ca[k].y); __stcg(q + 256, ca[k].z); __stcg(q + 288, ca[k].w);
-                __stcg(q + 320, cb[k].x); __stcg(q + 352, cb[k].y); __stcg(q + 384, cb[k].z); __stcg(q + 416, cb[k].w);
-                __stcg(q + 448, rw[k]);
+                uint32_t *q = sp + (size_t)k * FWD_RR_WORDS * LT;
+                __stcg(q, __float_as_uint(Mv1[k])); __stcg(q + LT, __float_as_uint(Iv1[k])); __stcg(q + 2 * LT, __float_as_uint(Dv1[k]));
+                __stcg(q + 3 * LT, __float_as_uint(dgv[k])); __stcg(q + 4 * LT, Mr1[k]); __stcg(q + 5 * LT, dgr[k]);
+                __stcg(q + 6 * LT, ca[k].x); __stcg(q + 7 * LT, ca[k].y); __stcg(q + 8 * LT, ca[k].z); __stcg(q + 9 * LT, ca[k].w);
+                __stcg(q + 10 * LT, cb[k].x); __stcg(q + 11 * LT, cb[k].y); __stcg(q + 12 * LT, cb[k].z); __stcg(q + 13 * LT, cb[k].w);
+                __stcg(q + 14 * LT, rw[k]);
             }
-            uint4 *rp = reinterpret_cast<uint4 *>(st + FWD_RR_HDR + (size_t)FWD_RR_WORDS * CPL * 32);
+            uint4 *rp = reinterpret_cast<uint4 *>(st + FWD_RR_HDR + (size_t)FWD_RR_WORDS * CPL * LT);
 #pragma unroll
-            for (int t = 0; t < NC / 4; t++) {
+            for (int t = wt; t < NC / 4; t += T) {
                 uint4 v;
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(wbase + (uint32_t)(t * 32 + lane) * 16u));
                 __stcg(rp + t * 32 + lane, v);
             }
-            if (lane == 0) { __stcg(st, (uint32_t)dEnd); __stcg(st + 1, (uint32_t)Id); __stcg(st + 2, (uint32_t)Dd); }
+            if (lane == 0 && wt == 0) { __stcg(st, (uint32_t)dEnd); __stcg(st + 1, (uint32_t)Id); __stcg(st + 2, (uint32_t)Dd); }
             __threadfence();
-            __syncwarp();
-            if (lane == 0) {
+            team_sync();      // every warp's part of the state is out (and fenced) before the chunk becomes runnable again
+            if (lane == 0 && wt == 0) {
+                __threadfence();
                 const int p2 = atomicAdd(a.rr_ctl + 1, 1);
                 __stcg(a.rr_q + (p2 & a.rr_mask), idx);
             }

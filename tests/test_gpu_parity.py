@@ -85,6 +85,23 @@ def test_one_warp_and_team_forms_of_the_forward_kernel(tables, golden, monkeypat
         eng.close()
 
 
+def test_time_sliced_teams_hand_chunks_back_and_resume(tables, monkeypatch):
+    """More chunks than resident teams, short slices (NPORE_RR_SLICE=64): a two-warp team saves its registers, team ring and
+    mailbox to HBM at a slice boundary, another team resumes the chunk -- outputs stay the reference's (r = 30 and r = 100)."""
+    from npore_b200.engine import Realigner
+    monkeypatch.setenv("NPORE_TEAM", "2")
+    monkeypatch.setenv("NPORE_RR_SLICE", "64")
+    S, NP = tables
+    rng = np.random.default_rng(97)
+    cm = synth.call_length_model(NP)
+    ref, tr = synth.make_reference_with_tracts(120_000, rng)
+    cases = [(rd[9], rd[7], cig.expand_cigar(rd[5])) for rd in synth.make_reads(ref, 100, 4000, rng, cm, tracts=tr)]
+    for r, mb in ((30, 100), (100, 300)):
+        eng = Realigner(S, NP, r=r, max_b_rows=mb)
+        _check(eng, cases, _oracle_all(cases, S, NP, r=r, max_b_rows=mb))
+        eng.close()
+
+
 def test_golden_sam_through_realign_reads(tables, golden, tmp_path):
     """bam.realign_reads on test/data/reads.sam + ref.fasta reproduces test/data/npore_realigned.sam, every field."""
     from npore_b200 import bam, cfg
