@@ -169,17 +169,21 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
     return NPORE_OK;
 }
 
-// Which instantiation runs a sub-batch of n chunks at band slots NC = 32 * nc32: one chunk per warp, or a team of two warps per
-// chunk (forward.cuh) -- for bands wider than 128 cells always (<4,2> instead of the 255-register <8,1>), otherwise when the
-// sub-batch has fewer chunks than half the warp slots of the one-warp form (latency-bound launches: C1, 50 k-row windows,
-// small file batches).  NPORE_TEAM=0/1 forces the choice (tests, A/B).
-inline int forward_team(const npore_ctx *ctx, int nc32, int n_sub)
+// Which instantiation runs a sub-batch at band slots NC = 32 * nc32: one chunk per warp, or a team of warps per chunk
+// (forward.cuh).  Measured on C4 (profiles/r02_ab_experiments.md): NC = 256 runs fastest as four-warp teams <2,4> (126 registers,
+// 16 warps/SM; <8,1> needs 255), NC = 128 as two-warp teams <2,2>; NC = 64 as one warp per chunk unless the sub-batch cannot fill
+// the warp slots -- judged by its effective parallelism par = (sum of chunk lengths) / (longest chunk), which is what bounds a
+// launch whose chunks never wait for a warp: teams when par <= 2/3 of the slots (C1, 50 k-row windows, small file batches; the
+// two forms are within 5% of each other around the threshold).
+// NPORE_TEAM=1/2/4 forces the choice (tests, A/B).
+inline int forward_team(const npore_ctx *ctx, int nc32, double par)
 {
     if (nc32 == 1) return 1;
-    if (const char *e = getenv("NPORE_TEAM")) { const int t = atoi(e); if (t == 1 || t == 2) return nc32 == 8 && t == 1 ? 1 : t; }
-    if (nc32 == 8) return 2;
-    const int slots = ctx->sm_count * (nc32 == 2 ? 16 : 12);          // resident one-warp chunks of <2,1> / <4,1>
-    return 2 * n_sub <= slots ? 2 : 1;
+    if (const char *e = getenv("NPORE_TEAM")) { const int t = atoi(e); if (t == 1 || t == 2) return t; if (t == 4) return nc32 == 8 ? 4 : 2; }
+    if (nc32 == 8) return 4;
+    if (nc32 == 4) return 2;
+    const int slots = ctx->sm_count * 16;          // resident one-warp chunks of <2,1>
+    return 3.0 * par <= 2.0 * (double)slots ? 2 : 1;
 }
 
 // BAM 4-bit bases -> base codes (cig.pyx:212-229 on the device): grid (items, parts)
@@ -561,12 +565,13 @@ static int run_pass(npore_ctx *ctx, uint32_t flags, bool wide, int *n_sat)
         aa.raw_ref = ctx->d_raw_ref.as<uint8_t>(); aa.raw_seq = ctx->d_raw_seq.as<uint8_t>();
         aa.colrec = ctx->d_colrec.as<uint4>(); aa.relaid = ctx->d_relaid.as<uint2>(); aa.rowrec = ctx->d_rowrec.as<uint32_t>();
         aa.max_n = ctx->P.max_n; aa.max_l = ctx->P.max_l; aa.nc = NC; aa.inf_row = ctx->P.np_rows;
-        const int team = forward_team(ctx, ctx->cpl, sb.count);       // warps per chunk of this sub-batch's forward launch
+        int bm = 1;
+        double bsum = 0.0;
+        for (int k = 0; k < sb.count; k++) { const int b = ctx->chunk_bmax[ctx->order[sb.first + k]]; bm = std::max(bm, b); bsum += b; }
+        const int team = forward_team(ctx, ctx->cpl, bsum / bm);      // warps per chunk of this sub-batch's forward launch
         aa.cpl = ctx->cpl / team;
         CU(cudaEventRecord(e0, ctx->stream));
         {   // equality words of all periods in dynamic shared memory: 6 planes of (longest slice / 32 + 2) words
-            int bm = 1;
-            for (int k = 0; k < sb.count; k++) bm = std::max(bm, ctx->chunk_bmax[ctx->order[sb.first + k]]);
             aa.e6_stride = (bm + 1 + 31) / 32 + 2;
             const size_t dyn = (size_t)NP_MAXN * aa.e6_stride * sizeof(uint32_t);
             if (dyn > 48 * 1024) CU(cudaFuncSetAttribute(annotate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
@@ -597,13 +602,15 @@ static int run_pass(npore_ctx *ctx, uint32_t flags, bool wide, int *n_sat)
         case 42: rc = launch_forward<2, 2, false>(ctx, fa, sb.count); break;
         case 81: rc = launch_forward<8, 1, false>(ctx, fa, sb.count); break;
         case 82: rc = launch_forward<4, 2, false>(ctx, fa, sb.count); break;
+        case 84: rc = launch_forward<2, 4, false>(ctx, fa, sb.count); break;
         // the fallback for a batch in which a traceback met a saturated n-polymer run (forward.cuh: WIDE)
         case -11: rc = launch_forward<1, 1, true>(ctx, fa, sb.count); break;
         case -21: rc = launch_forward<2, 1, true>(ctx, fa, sb.count); break;
         case -22: rc = launch_forward<1, 2, true>(ctx, fa, sb.count); break;
         case -41: rc = launch_forward<4, 1, true>(ctx, fa, sb.count); break;
         case -42: rc = launch_forward<2, 2, true>(ctx, fa, sb.count); break;
-        default: rc = launch_forward<4, 2, true>(ctx, fa, sb.count); break;      // (-81 too: the two-warp form carries W > 128)
+        case -82: rc = launch_forward<4, 2, true>(ctx, fa, sb.count); break;
+        default: rc = launch_forward<2, 4, true>(ctx, fa, sb.count); break;      // (-84, and -81: a team form carries W > 128)
         }
         if (rc != NPORE_OK) return rc;
         S.launches++;

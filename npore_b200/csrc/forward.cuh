@@ -167,7 +167,7 @@ __device__ __forceinline__ float fmin3(float a, float b, float c)
 // unsaturated (16 bits, max_b_rows <= 65000), a record whose LEN/SHR run does not fit the 11-bit field stores 2047 and its true run
 // goes to an overflow list the traceback consults.  Same arithmetic otherwise; api.cu re-runs a batch with WIDE only when needed.
 template <int CPL, int T, bool WIDE = false>
-__global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, CPL <= 2 ? FWD_MINB : (CPL == 4 && T == 1) ? 2 : 1) forward_kernel(const ForwardArgs a)
+__global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 ? FWD_MINB : (CPL == 4 && T == 1) ? 2 : 1) forward_kernel(const ForwardArgs a)
 {
     constexpr uint32_t SAT16 = WIDE ? 0xffff0000u : FWD_SAT16;        // saturation of the carried LEN / SHR runs (<< 16)
     constexpr int NC = 32 * CPL * T;

@@ -60,7 +60,7 @@ def test_fuzz_golden_reference_outputs(tables, golden, engine_factory):
         _check(eng, [(c["ref"], c["seq"], c["cigar"]) for c in cases], want)
 
 
-@pytest.mark.parametrize("team", ["1", "2"])
+@pytest.mark.parametrize("team", ["1", "2", "4"])
 def test_one_warp_and_team_forms_of_the_forward_kernel(tables, golden, monkeypatch, team):
     """forward_kernel<CPL, T>: one chunk per warp (T = 1) and a two-warp team per chunk (T = 2: band split across the warps, team
     ring, mailbox, named barrier) forced through NPORE_TEAM -- both must reproduce the reference's outputs (CIGARs, chunk scores,
@@ -86,19 +86,22 @@ def test_one_warp_and_team_forms_of_the_forward_kernel(tables, golden, monkeypat
 
 
 def test_time_sliced_teams_hand_chunks_back_and_resume(tables, monkeypatch):
-    """More chunks than resident teams, short slices (NPORE_RR_SLICE=64): a two-warp team saves its registers, team ring and
-    mailbox to HBM at a slice boundary, another team resumes the chunk -- outputs stay the reference's (r = 30 and r = 100)."""
+    """More chunks than resident teams, short slices (NPORE_RR_SLICE=64): a team of two or four warps saves its registers, team
+    ring and mailbox to HBM at a slice boundary, another team resumes the chunk -- outputs stay the reference's."""
     from npore_b200.engine import Realigner
-    monkeypatch.setenv("NPORE_TEAM", "2")
     monkeypatch.setenv("NPORE_RR_SLICE", "64")
     S, NP = tables
     rng = np.random.default_rng(97)
     cm = synth.call_length_model(NP)
     ref, tr = synth.make_reference_with_tracts(120_000, rng)
     cases = [(rd[9], rd[7], cig.expand_cigar(rd[5])) for rd in synth.make_reads(ref, 100, 4000, rng, cm, tracts=tr)]
-    for r, mb in ((30, 100), (100, 300)):
+    want = {}
+    for team, r, mb in (("2", 30, 100), ("2", 60, 200), ("2", 100, 300), ("4", 100, 300)):      # <1,2>, <2,2>, <4,2>, <2,4>
+        monkeypatch.setenv("NPORE_TEAM", team)
+        if (r, mb) not in want:
+            want[(r, mb)] = _oracle_all(cases, S, NP, r=r, max_b_rows=mb)
         eng = Realigner(S, NP, r=r, max_b_rows=mb)
-        _check(eng, cases, _oracle_all(cases, S, NP, r=r, max_b_rows=mb))
+        _check(eng, cases, want[(r, mb)])
         eng.close()
 
 

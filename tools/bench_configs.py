@@ -66,7 +66,8 @@ def main():
     for L in lens:
         reads += synth.make_reads(ref, 1, int(L), rng, cm, tracts=tr)
     cases = [(rd[9], rd[7], cig.expand_cigar(rd[5])) for rd in reads]
-    for r in (10, 30, 60, 100):
+    radii = tuple(int(x) for x in os.environ["NPORE_CFG_R"].split(",")) if os.environ.get("NPORE_CFG_R") else (10, 30, 60, 100)
+    for r in radii:
         for mb in (5000, 20000, 50000):
             eng = Realigner(S, NP, r=r, max_b_rows=mb)
             st, tk, te, res = run(eng, cases, NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED, reps=2)
