@@ -299,7 +299,7 @@ def select_reads(bam, regions=None, max_reads=0):
             yield ctg, sel
 
 
-def _append_blob(fd, offset, blob, pool, pieces=4):
+def _append_blob(fd, offset, blob, pool, pieces=int(os.environ.get("NPORE_WRITE_PIECES", "4"))):
     """Append `blob` (uint8 array) to the file at `offset` with a few concurrent pwrite calls: the copy into the page cache is a
     single-core memcpy otherwise (62 MB of SAM text per 3,000 reads = 14 ms; 4 ms with four).  Returns the new end offset."""
     mv = memoryview(blob)
@@ -419,6 +419,7 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
     tm = timings if timings is not None else {}
     for k in ("open", "gather", "gpu_wait", "format", "write", "concat"):
         tm.setdefault(k, 0.0)
+    _keep_freed_buffers_mapped()
     t0 = time.perf_counter()
     if out_prefix is not None:
         cfg.args.out_prefix = out_prefix
@@ -493,10 +494,31 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
 
 import threading as _threading  # noqa: E402
 _PIPE_LOCK = _threading.Lock()
+_MALLOC_TUNED = False
+
+
+def _keep_freed_buffers_mapped():
+    """Once per process: raise glibc's mmap / trim thresholds (mallopt) so that the pipeline's per-window buffers -- nibble and
+    CIGAR gathers, SAM text columns, result arrays, the 20 MB SAM blob -- are recycled from the heap instead of being mmap'ed,
+    page-faulted by 16 threads at once and munmap'ed again for every window.  Measured on the C2 file (16 host cores): the
+    gathers in front of the second and third upload took 8-12 ms instead of 1 ms (page faults + address-space lock beside the
+    inflating prefetch threads), the whole file 67 -> 64 ms with the GPU, not the host, the limiter afterwards
+    (profiles/r02_ab_experiments.md).  NPORE_NO_MALLOPT=1 leaves the allocator alone."""
+    global _MALLOC_TUNED
+    if _MALLOC_TUNED or os.environ.get("NPORE_NO_MALLOPT"):
+        return
+    _MALLOC_TUNED = True
+    try:
+        import ctypes
+        libc = ctypes.CDLL("libc.so.6")
+        libc.mallopt(-3, 32 << 20)            # M_MMAP_THRESHOLD: its maximum (blocks up to 32 MB come from the heap)
+        libc.mallopt(-1, 1 << 30)             # M_TRIM_THRESHOLD: keep up to 1 GB of freed heap
+    except (OSError, AttributeError):         # not glibc
+        pass
 
 
 def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=None, max_batch_ops=64_000_000, n_threads=0,
-                timings=None, window_bytes=16 << 20, n_inflight=2, devices=None):
+                timings=None, window_bytes=16 << 20, n_inflight=3, devices=None):
     """realign.py:75-115 without pysam / Pool: header, ingest, GPU realignment, records appended in input order
     (= coordinate order for a sorted BAM, which is what the header claims).  Returns the number of records written.
     Flat arrays all the way, as a pipeline: the reader streams the file in windows of ~window_bytes of inflated records
@@ -517,6 +539,7 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
     tm = timings if timings is not None else {}
     for k in ("open", "gather", "gpu_wait", "format", "write"):
         tm.setdefault(k, 0.0)
+    _keep_freed_buffers_mapped()
     t0 = time.perf_counter()
     trace = tm.get("trace")                       # optional list: (seconds since the call, event) of every pipeline step
     mark = (lambda ev: trace.append((round(time.perf_counter() - t0, 5), ev))) if trace is not None else (lambda ev: None)
@@ -545,7 +568,7 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
         path = f"{cfg.args.out_prefix}.sam"
         fd = os.open(path, os.O_WRONLY)
         end = os.path.getsize(path)                       # the header is there already
-        with ThreadPoolExecutor(4) as wpool:
+        with ThreadPoolExecutor(int(os.environ.get("NPORE_WRITE_PIECES", "4"))) as wpool:
             while True:
                 item = pending.get()
                 if item is None:
@@ -558,7 +581,9 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
                     t1 = time.perf_counter()
                     res, st_ = fut.result()
                     t2 = time.perf_counter()
-                    mark(f"gpu done n={n} kernels_ms={st_['ms_kernels_total']:.1f} h2d_ms={st_['ms_h2d']:.1f} warps/SM={st_['fwd_warps_per_sm']}")
+                    mark(f"gpu done n={n} kernels_ms={st_['ms_kernels_total']:.1f} h2d_ms={st_['ms_h2d']:.1f} plan_ms={st_['ms_plan']:.1f} d2h_ms={st_['ms_d2h']:.1f} "
+                         f"warps/SM={st_['fwd_warps_per_sm']} context from {1e3 * (st_['wall'][0] - t0):.1f} ms, buffers {1e3 * (st_['wall'][1] - t0):.1f}, "
+                         f"to {1e3 * (st_['wall'][2] - t0):.1f} ms")
                     _report(res.status[:n], "realign_read")
                     blob = format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols)
                     t3 = time.perf_counter()
@@ -595,7 +620,9 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
                     part = sel[cut:stop]
                     t1 = time.perf_counter()
                     nib, nib_start = bam.gather_nib(part, n_threads)          # the upload: BAM's own 4-bit bases + CIGAR words
+                    mark("nib gathered")
                     cig_words, cig_off = bam.gather_cigar(part, n_threads)
+                    mark("cigar gathered")
                     lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
                     packed = PackedBatch.from_flat_shared_nib(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
                                                               nib, nib_start, bam.aln_len[part], cig_words, cig_off)

@@ -69,6 +69,7 @@ struct HostBuf {      // pinned staging owned by the library (download path)
 
 struct SubBatch { int first, count; };
 
+std::atomic<long long> g_par_inflight[64];  // effective parallelism (forward_team) of the forward launches in flight per device, all contexts
 std::atomic<int> g_ctx_on_device[64];      // live contexts per device: they share the scratch budget (PipelinedRealigner)
 
 }  // namespace
@@ -171,19 +172,23 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 
 // Which instantiation runs a sub-batch at band slots NC = 32 * nc32: one chunk per warp, or a team of warps per chunk
 // (forward.cuh).  Measured on C4 (profiles/r02_ab_experiments.md): NC = 256 runs fastest as four-warp teams <2,4> (126 registers,
-// 16 warps/SM; <8,1> needs 255), NC = 128 as two-warp teams <2,2>; NC = 64 as one warp per chunk unless the sub-batch cannot fill
+// 16 warps/SM; <8,1> needs 255), NC = 128 as two-warp teams <2,2>; NC = 64 as one warp per chunk unless the launch cannot fill
 // the warp slots -- judged by its effective parallelism par = (sum of chunk lengths) / (longest chunk), which is what bounds a
-// launch whose chunks never wait for a warp: teams when par <= 2/3 of the slots (C1, 50 k-row windows, small file batches; the
-// two forms are within 5% of each other around the threshold).
-// NPORE_TEAM=1/2/4 forces the choice (tests, A/B).
-inline int forward_team(const npore_ctx *ctx, int nc32, double par)
+// launch whose chunks never wait for a warp.  Alone on the device: teams when par <= 2/3 of the slots (C1, 50 k-row windows; the
+// two forms are within 5% of each other around the threshold).  Beside other contexts (live on the device, or `others` = the par
+// of their launches in flight: PipelinedRealigner, the file pipeline) the one-warp form is the better neighbour -- a 1,000-read batch takes 14.2 instead of
+// 13.6 ms but leaves 60% of the warp slots to the next batch instead of 20% -- so teams only while everything in flight together
+// is below a quarter of the slots.  NPORE_TEAM=1/2/4 forces the choice (tests, A/B).
+inline int forward_team(const npore_ctx *ctx, int nc32, double par, double others)
 {
     if (nc32 == 1) return 1;
     if (const char *e = getenv("NPORE_TEAM")) { const int t = atoi(e); if (t == 1 || t == 2) return t; if (t == 4) return nc32 == 8 ? 4 : 2; }
     if (nc32 == 8) return 4;
     if (nc32 == 4) return 2;
-    const int slots = ctx->sm_count * 16;          // resident one-warp chunks of <2,1>
-    return 3.0 * par <= 2.0 * (double)slots ? 2 : 1;
+    const double slots = ctx->sm_count * 16.0;          // resident one-warp chunks of <2,1>
+    const bool siblings = ctx->device < 64 && g_ctx_on_device[ctx->device].load() > 1;      // a pipeline: the next batch is on its way
+    if (others > 0.0 || siblings) return 4.0 * (par + others) <= slots ? 2 : 1;
+    return 3.0 * par <= 2.0 * slots ? 2 : 1;
 }
 
 // BAM 4-bit bases -> base codes (cig.pyx:212-229 on the device): grid (items, parts)
@@ -464,6 +469,12 @@ static int run_pass(npore_ctx *ctx, uint32_t flags, bool wide, int *n_sat)
         npore_ctx *c; bool ok = false;
         ~RunGuard() { if (!ok) { cudaStreamSynchronize(c->stream); cudaGetLastError(); c->ran = false; } }
     } guard{ctx};
+    // this pass's entry in g_par_inflight: set per sub-batch, withdrawn when the pass has synchronised (or failed)
+    struct InFlight {
+        std::atomic<long long> *g; long long mine = 0;
+        long long set(long long par) { const long long before = g ? g->fetch_add(par - mine) : mine; const long long o = before - mine; mine = par; return o > 0 ? o : 0; }
+        ~InFlight() { if (g && mine) g->fetch_sub(mine); }
+    } inflight{ctx->device < 64 ? &g_par_inflight[ctx->device] : nullptr};
     const int n = (int)ctx->items.size();
     const int64_t nchunks = ctx->n_chunks;
     const int NC = 32 * ctx->cpl;
@@ -568,7 +579,9 @@ static int run_pass(npore_ctx *ctx, uint32_t flags, bool wide, int *n_sat)
         int bm = 1;
         double bsum = 0.0;
         for (int k = 0; k < sb.count; k++) { const int b = ctx->chunk_bmax[ctx->order[sb.first + k]]; bm = std::max(bm, b); bsum += b; }
-        const int team = forward_team(ctx, ctx->cpl, bsum / bm);      // warps per chunk of this sub-batch's forward launch
+        const long long par = (long long)(bsum / bm) + 1;
+        const long long others = inflight.set(par);                  // the other contexts' launches on this device
+        const int team = forward_team(ctx, ctx->cpl, (double)par, (double)others);      // warps per chunk of this sub-batch's forward launch
         aa.cpl = ctx->cpl / team;
         CU(cudaEventRecord(e0, ctx->stream));
         {   // equality words of all periods in dynamic shared memory: 6 planes of (longest slice / 32 + 2) words

@@ -441,10 +441,16 @@ class PipelinedRealigner:
     def submit(self, packed: PackedBatch, flags: int = 0, result: BatchResult = None, pinned_result=False):
         """Future of (BatchResult, stats dict) for npore_align_batch on the next free context."""
         def work():
+            import time
             eng = self._free.get()
             try:
-                res = eng.align_packed(packed, flags, result or eng.new_result(packed, flags, pinned=pinned_result))
-                return res, eng.stats()
+                t0 = time.perf_counter()
+                out = result or eng.new_result(packed, flags, pinned=pinned_result)
+                t1 = time.perf_counter()
+                res = eng.align_packed(packed, flags, out)
+                st = eng.stats()
+                st["wall"] = (t0, t1, time.perf_counter())      # context acquired, result buffers ready, batch done (perf_counter)
+                return res, st
             finally:
                 self._free.put(eng)
         return self._pool.submit(work)

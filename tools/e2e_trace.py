@@ -10,7 +10,7 @@ cfg.args.sub_scores, cfg.args.np_scores = S, NP
 ref, reads = bench.make_workload(20260101, 1_000_000, n, 10000, NP)
 bench.write_fixture_bam("/tmp/c2.bam", ref, reads)
 fa = {"chr1": ref}
-for rep in range(3):
+for rep in range(int(os.environ.get('NPORE_REPS', '3'))):
     tm = {"trace": []}
     t = time.perf_counter()
     bamio.realign_bam("/tmp/c2.bam", fa, out_prefix="/tmp/c2_out", argv=["x"], timings=tm)
