@@ -9,7 +9,7 @@
  *                                           src/bam.pyx:18-47 get_read_data(): flag, reference_start, reference_length,
  *                                           mapping_quality, cigar, query_alignment_sequence / _qualities (soft clips
  *                                           removed), HP tag.  BGZF members are inflated on n_threads host threads.
- *   npore_sam_format                     <- the record print of src/bam.pyx:81-84 realign_read():
+ *   npore_sam_format / npore_sam_format_fd <- the record print of src/bam.pyx:81-84 realign_read():
  *                                           name flag rname start+1 mapq CIGAR * 0 (stop-start) seq quals HP:i:hap
  *                                           for a whole batch, in input order, from the run-length words the GPU returns.
  *
@@ -83,6 +83,17 @@ int64_t  npore_sam_format(int64_t n, int n_threads,
                           const uint32_t *rle, const int64_t *rle_off,
                           const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
                           const int32_t *hp, uint8_t *out, int64_t out_capacity);
+/* npore_sam_format + the append to the output file (the `print(..., file=fh)` of src/bam.pyx:81-84) in one pass: every formatter
+ * thread pwrite()s its finished slice of records to `fd` at file_offset + (its offset inside the block) while the others still
+ * format -- the copy into the page cache runs on all threads and overlaps the formatting.  `scratch` (>= npore_sam_bound bytes)
+ * holds the text meanwhile.  Returns the number of bytes appended; the caller advances its end-of-file offset by it. */
+int64_t  npore_sam_format_fd(int64_t n, int n_threads,
+                             const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
+                             const uint8_t *ref_names, const int64_t *ref_name_off, int32_t n_refs,
+                             const int32_t *pos, const int32_t *end, const int32_t *mapq,
+                             const uint32_t *rle, const int64_t *rle_off,
+                             const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
+                             const int32_t *hp, uint8_t *scratch, int64_t scratch_capacity, int fd, int64_t file_offset);
 
 #ifdef __cplusplus
 }

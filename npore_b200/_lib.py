@@ -51,7 +51,7 @@ EXPORTS = ["npore_ctx_create", "npore_ctx_destroy", "npore_set_stream", "npore_c
            "npore_align_batch", "npore_get_np_info", "npore_get_np_info_batch", "npore_confusion_batch", "npore_last_stats", "npore_strerror", "npore_last_error", "npore_version"]
 
 IO_EXPORTS = ["npore_io_last_error", "npore_bam_open", "npore_bam_advance", "npore_bam_prefetch", "npore_bam_close", "npore_bam_header_text", "npore_bam_n_refs", "npore_bam_ref",
-              "npore_bam_n_records", "npore_bam_columns", "npore_bam_gather", "npore_bam_gather_nib", "npore_sam_bound", "npore_sam_format"]
+              "npore_bam_n_records", "npore_bam_columns", "npore_bam_gather", "npore_bam_gather_nib", "npore_sam_bound", "npore_sam_format", "npore_sam_format_fd"]
 
 _lib = None
 
@@ -106,5 +106,7 @@ def lib():
         L.npore_sam_bound.restype = C.c_int64
         L.npore_sam_format.argtypes = [C.c_int64, C.c_int] + [vp] * 6 + [C.c_int32] + [vp] * 11 + [C.c_int64]
         L.npore_sam_format.restype = C.c_int64
+        L.npore_sam_format_fd.argtypes = [C.c_int64, C.c_int] + [vp] * 6 + [C.c_int32] + [vp] * 11 + [C.c_int64, C.c_int, C.c_int64]
+        L.npore_sam_format_fd.restype = C.c_int64
         _lib = L
     return _lib

@@ -251,9 +251,10 @@ class NativeBam:
         return o
 
 
-def format_sam(bam, sel, g, rle, rle_off, n_threads=0, cols=None):
+def format_sam(bam, sel, g, rle, rle_off, n_threads=0, cols=None, fd=None, offset=0):
     """bam.pyx:83 for the selected records as one bytes-like block (npore_sam_format).  cols: the records' column values
-    taken earlier (dict of int32 arrays: flag ref_id pos end mapq has_qual hp) when the reader has moved on since."""
+    taken earlier (dict of int32 arrays: flag ref_id pos end mapq has_qual hp) when the reader has moved on since.
+    fd: also append the block to that file descriptor at `offset` while formatting (npore_sam_format_fd)."""
     L = bam._L
     names = "".join(n for n, _ in bam.refs).encode()
     rn_off = np.concatenate(([0], np.cumsum([len(n.encode()) for n, _ in bam.refs], dtype=np.int64)))
@@ -269,10 +270,11 @@ def format_sam(bam, sel, g, rle, rle_off, n_threads=0, cols=None):
     qual = g["qual_ascii"] if g["qual_ascii"] is not None else g["seq_ascii"]
     if g["qual_ascii"] is None:
         hq = np.zeros_like(hq)
-    got = L.npore_sam_format(n, n_threads, g["names"].ctypes.data, g["name_off"].ctypes.data, flag.ctypes.data, ref_id.ctypes.data,
-                             rn.ctypes.data, rn_off.ctypes.data, len(bam.refs), pos.ctypes.data, end.ctypes.data, mapq.ctypes.data,
-                             rle.ctypes.data if len(rle) else None, rle_off.ctypes.data, g["seq_ascii"].ctypes.data, qual.ctypes.data,
-                             g["seq_off"].ctypes.data, hq.ctypes.data, hp.ctypes.data, out.ctypes.data, cap)
+    args = (n, n_threads, g["names"].ctypes.data, g["name_off"].ctypes.data, flag.ctypes.data, ref_id.ctypes.data,
+            rn.ctypes.data, rn_off.ctypes.data, len(bam.refs), pos.ctypes.data, end.ctypes.data, mapq.ctypes.data,
+            rle.ctypes.data if len(rle) else None, rle_off.ctypes.data, g["seq_ascii"].ctypes.data, qual.ctypes.data,
+            g["seq_off"].ctypes.data, hq.ctypes.data, hp.ctypes.data, out.ctypes.data, cap)
+    got = L.npore_sam_format(*args) if fd is None else L.npore_sam_format_fd(*args, int(fd), int(offset))
     if got < 0:
         raise RuntimeError(L.npore_io_last_error().decode())
     return out[:got]
@@ -299,21 +301,6 @@ def select_reads(bam, regions=None, max_reads=0):
             yield ctg, sel
 
 
-def _append_blob(fd, offset, blob, pool, pieces=int(os.environ.get("NPORE_WRITE_PIECES", "4"))):
-    """Append `blob` (uint8 array) to the file at `offset` with a few concurrent pwrite calls: the copy into the page cache is a
-    single-core memcpy otherwise (62 MB of SAM text per 3,000 reads = 14 ms; 4 ms with four).  Returns the new end offset."""
-    mv = memoryview(blob)
-    n = len(mv)
-    if n < (8 << 20) or pool is None:
-        os.pwrite(fd, mv, offset)
-        return offset + n
-    step = -(-n // pieces)
-    futs = [pool.submit(os.pwrite, fd, mv[a:a + step], offset + a) for a in range(0, n, step)]
-    for f in futs:
-        f.result()
-    return offset + n
-
-
 _PIPES = {}
 
 
@@ -336,7 +323,7 @@ def _read_loads(bam, sel, max_b_rows=20000, r=30):
     return (ops + -(-ops // (max_b_rows - 1))) * (2 * r + 1)
 
 
-def _realign_segments(bam, segments, fa, codes, codes_lock, pipe, fh, tm, n_threads, max_batch_ops, n_inflight):
+def _realign_segments(bam, segments, fa, pipe, fh, tm, n_threads, max_batch_ops, n_inflight):
     """The three-stage pipeline over an explicit list of (contig, record indices) segments: gather batch k+1 while batch k is
     on the GPU and batch k-1 is formatted and written to `fh` -- records in segment order.  Returns the records written."""
     import queue
@@ -362,9 +349,10 @@ def _realign_segments(bam, segments, fa, codes, codes_lock, pipe, fh, tm, n_thre
                 res, _ = fut.result()
                 t2 = time.perf_counter()
                 _report(res.status[:n], "realign_read")
-                blob = format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols)
+                fh.flush()
+                end = os.fstat(fh.fileno()).st_size
+                format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols, fd=fh.fileno(), offset=end)
                 t3 = time.perf_counter()
-                fh.write(memoryview(blob))
                 tm["gpu_wait"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += time.perf_counter() - t3
                 state["written"] += n
             except Exception as e:                    # noqa: BLE001
@@ -374,10 +362,7 @@ def _realign_segments(bam, segments, fa, codes, codes_lock, pipe, fh, tm, n_thre
     retire.start()
     try:
         for ctg, sel in segments:
-            with codes_lock:
-                if ctg not in codes:
-                    codes[ctg] = bases_to_int(fa[ctg].upper())
-                cc = codes[ctg]
+            contig = fa[ctg]
             ops = np.cumsum((bam.end[sel] - bam.pos[sel]).astype(np.int64) + bam.aln_len[sel])
             cut = 0
             while cut < len(sel) and state["error"] is None:
@@ -387,7 +372,7 @@ def _realign_segments(bam, segments, fa, codes, codes_lock, pipe, fh, tm, n_thre
                 nib, nib_start = bam.gather_nib(part, n_threads)              # the upload: BAM's own 4-bit bases + CIGAR words
                 cig_words, cig_off = bam.gather_cigar(part, n_threads)
                 lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
-                packed = PackedBatch.from_flat_shared_nib(cc[lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
+                packed = PackedBatch.from_flat_shared_nib(bases_to_int(contig[lo:hi].upper()), bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
                                                           nib, nib_start, bam.aln_len[part], cig_words, cig_off)
                 fut = pipe.submit(packed, flags)                              # the GPU starts; the SAM-text gather runs beside it
                 g = bam.gather(part, n_threads, want_codes=False, want_cigar=False)      # ASCII bases / qualities / names
@@ -447,7 +432,6 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
             shard_load[int(gidx)] += int(ld[m].sum())
         done += float(ld.sum())
     tm["open"] += time.perf_counter() - t0
-    codes, codes_lock = {}, threading.Lock()
     parts = [out if g == 0 else f"{cfg.args.out_prefix}.part{g}.sam" for g in range(G)]
     results = [None] * G
     thread_tm = [{k: 0.0 for k in ("gather", "gpu_wait", "format", "write")} for _ in range(G)]
@@ -457,7 +441,7 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
         try:
             pipe = _pipeline(sub, npt, n_inflight, devices[g])
             with open(parts[g], "ab" if g == 0 else "wb") as fh:
-                n = _realign_segments(bam, shard_segs[g], fa, codes, codes_lock, pipe, fh, thread_tm[g], max(1, (n_threads or os.cpu_count() or 1) // G),
+                n = _realign_segments(bam, shard_segs[g], fa, pipe, fh, thread_tm[g], max(1, (n_threads or os.cpu_count() or 1) // G),
                                       max_batch_ops, n_inflight)
             results[g] = (n, time.perf_counter() - t1, None)
         except Exception as e:      # noqa: BLE001
@@ -556,7 +540,6 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
     sub, npt = _tables()
     pipe = _pipeline(sub, npt, n_inflight, devices[0] if devices else None)
     flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED
-    codes = {}
     tm["open"] += time.perf_counter() - t0
     mark("opened")
     # stage 3 (own thread): wait for batch k, format its records, append them to the SAM -- in submit order
@@ -564,38 +547,34 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
     state = {"written": 0, "error": None}
 
     def retire_loop():
-        from concurrent.futures import ThreadPoolExecutor
         path = f"{cfg.args.out_prefix}.sam"
         fd = os.open(path, os.O_WRONLY)
         end = os.path.getsize(path)                       # the header is there already
-        with ThreadPoolExecutor(int(os.environ.get("NPORE_WRITE_PIECES", "4"))) as wpool:
-            while True:
-                item = pending.get()
-                if item is None:
-                    os.close(fd)
-                    return
-                if state["error"] is not None:
-                    continue                              # keep draining so that the producer never blocks
-                try:
-                    fut, cols, g, n = item
-                    t1 = time.perf_counter()
-                    res, st_ = fut.result()
-                    t2 = time.perf_counter()
-                    mark(f"gpu done n={n} kernels_ms={st_['ms_kernels_total']:.1f} h2d_ms={st_['ms_h2d']:.1f} plan_ms={st_['ms_plan']:.1f} d2h_ms={st_['ms_d2h']:.1f} "
-                         f"warps/SM={st_['fwd_warps_per_sm']} context from {1e3 * (st_['wall'][0] - t0):.1f} ms, buffers {1e3 * (st_['wall'][1] - t0):.1f}, "
-                         f"to {1e3 * (st_['wall'][2] - t0):.1f} ms")
-                    _report(res.status[:n], "realign_read")
-                    blob = format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols)
-                    t3 = time.perf_counter()
-                    mark("formatted")
-                    end = _append_blob(fd, end, blob, wpool)
-                    mark("written")
-                    tm["gpu_wait"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += time.perf_counter() - t3
-                    state["written"] += n
-                    with cfg.counter.get_lock():
-                        cfg.counter.value += n
-                except Exception as e:                    # noqa: BLE001
-                    state["error"] = e
+        while True:
+            item = pending.get()
+            if item is None:
+                os.close(fd)
+                return
+            if state["error"] is not None:
+                continue                              # keep draining so that the producer never blocks
+            try:
+                fut, cols, g, n = item
+                t1 = time.perf_counter()
+                res, st_ = fut.result()
+                t2 = time.perf_counter()
+                mark(f"gpu done n={n} kernels_ms={st_['ms_kernels_total']:.1f} h2d_ms={st_['ms_h2d']:.1f} plan_ms={st_['ms_plan']:.1f} d2h_ms={st_['ms_d2h']:.1f} "
+                     f"warps/SM={st_['fwd_warps_per_sm']} context from {1e3 * (st_['wall'][0] - t0):.1f} ms, buffers {1e3 * (st_['wall'][1] - t0):.1f}, "
+                     f"to {1e3 * (st_['wall'][2] - t0):.1f} ms")
+                _report(res.status[:n], "realign_read")
+                end += len(format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols, fd=fd, offset=end))
+                t3 = time.perf_counter()
+                mark("formatted + written")
+                tm["gpu_wait"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += time.perf_counter() - t3
+                state["written"] += n
+                with cfg.counter.get_lock():
+                    cfg.counter.value += n
+            except Exception as e:                    # noqa: BLE001
+                state["error"] = e
 
     retire = threading.Thread(target=retire_loop, daemon=True)
     retire.start()
@@ -611,8 +590,7 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
                     break
             for ctg, sel in select_reads(bam, regions, (max_reads - kept) if max_reads else 0):
                 kept += len(sel)
-                if ctg not in codes:
-                    codes = {ctg: bases_to_int(fa[ctg].upper())}            # one contig resident at a time
+                contig = fa[ctg]
                 ops = np.cumsum((bam.end[sel] - bam.pos[sel]).astype(np.int64) + bam.aln_len[sel])
                 cut = 0
                 while cut < len(sel) and state["error"] is None:
@@ -624,7 +602,8 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
                     cig_words, cig_off = bam.gather_cigar(part, n_threads)
                     mark("cigar gathered")
                     lo, hi = int(bam.pos[part].min()), int(bam.end[part].max())
-                    packed = PackedBatch.from_flat_shared_nib(codes[ctg][lo:hi], bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
+                    # base codes of the batch's reference span only (not the contig: 250 Mb of chr1 for a window that covers 1 Mb)
+                    packed = PackedBatch.from_flat_shared_nib(bases_to_int(contig[lo:hi].upper()), bam.pos[part].astype(np.int64) - lo, bam.end[part] - bam.pos[part],
                                                               nib, nib_start, bam.aln_len[part], cig_words, cig_off)
                     fut = pipe.submit(packed, flags)                          # the GPU starts; the SAM-text gather runs beside it
                     mark(f"submitted n={len(part)}")

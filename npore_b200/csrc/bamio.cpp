@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -480,13 +481,13 @@ int64_t npore_sam_bound(int64_t n, const int64_t *name_off, const int64_t *seq_o
     return (name_off[n] - name_off[0]) + 2 * (seq_off[n] - seq_off[0]) + 10 * (rle_off[n] - rle_off[0]) + n * (72 + max_ref_name);
 }
 
-int64_t npore_sam_format(int64_t n, int n_threads,
+static int64_t sam_format_impl(int64_t n, int n_threads,
                          const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
                          const uint8_t *ref_names, const int64_t *ref_name_off, int32_t n_refs,
                          const int32_t *pos, const int32_t *end, const int32_t *mapq,
                          const uint32_t *rle, const int64_t *rle_off,
                          const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
-                         const int32_t *hp, uint8_t *out, int64_t out_capacity)
+                         const int32_t *hp, uint8_t *out, int64_t out_capacity, int fd, int64_t file_off)
 {
     if (n < 0) return io_fail(NPORE_IO_ERR_ARG, "negative count");
     if (!n) return 0;
@@ -518,6 +519,7 @@ int64_t npore_sam_format(int64_t n, int n_threads,
     for (int64_t k = 0; k < n; k++) at[(size_t)k + 1] += at[(size_t)k];
     if (at[(size_t)n] > out_capacity) return io_fail(NPORE_IO_ERR_ARG, "output buffer too small (use npore_sam_bound)");
     // pass 2: write
+    std::atomic<int> wr_err{0};
     parallel_for(n, n_threads, [&](int64_t lo, int64_t hi) {
         for (int64_t k = lo; k < hi; k++) {
             uint8_t *o = out + at[(size_t)k];
@@ -541,8 +543,43 @@ int64_t npore_sam_format(int64_t n, int n_threads,
             std::memcpy(o, "HP:i:", 5); o += 5;
             o = put_dec(o, hp[k]); *o++ = '\n';
         }
+        if (fd >= 0) {      // the slice is complete: straight into the file, beside the other threads' formatting and writes
+            const uint8_t *p = out + at[(size_t)lo];
+            int64_t left = at[(size_t)hi] - at[(size_t)lo], off = file_off + at[(size_t)lo];
+            while (left > 0) {
+                const ssize_t w = pwrite(fd, p, (size_t)left, (off_t)off);
+                if (w < 0) { if (errno == EINTR) continue; wr_err = errno ? errno : EIO; break; }
+                p += w; left -= w; off += w;
+            }
+        }
     });
+    if (wr_err) return io_fail(NPORE_IO_ERR_OPEN, std::string("pwrite failed: ") + std::strerror(wr_err));
     return at[(size_t)n];
+}
+
+int64_t npore_sam_format(int64_t n, int n_threads,
+                         const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
+                         const uint8_t *ref_names, const int64_t *ref_name_off, int32_t n_refs,
+                         const int32_t *pos, const int32_t *end, const int32_t *mapq,
+                         const uint32_t *rle, const int64_t *rle_off,
+                         const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
+                         const int32_t *hp, uint8_t *out, int64_t out_capacity)
+{
+    return sam_format_impl(n, n_threads, names, name_off, flag, ref_id, ref_names, ref_name_off, n_refs, pos, end, mapq, rle, rle_off,
+                           seq_ascii, qual_ascii, seq_off, has_qual, hp, out, out_capacity, -1, 0);
+}
+
+int64_t npore_sam_format_fd(int64_t n, int n_threads,
+                            const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
+                            const uint8_t *ref_names, const int64_t *ref_name_off, int32_t n_refs,
+                            const int32_t *pos, const int32_t *end, const int32_t *mapq,
+                            const uint32_t *rle, const int64_t *rle_off,
+                            const uint8_t *seq_ascii, const uint8_t *qual_ascii, const int64_t *seq_off, const int32_t *has_qual,
+                            const int32_t *hp, uint8_t *scratch, int64_t scratch_capacity, int fd, int64_t file_offset)
+{
+    if (fd < 0 || file_offset < 0) return io_fail(NPORE_IO_ERR_ARG, "bad file descriptor / offset");
+    return sam_format_impl(n, n_threads, names, name_off, flag, ref_id, ref_names, ref_name_off, n_refs, pos, end, mapq, rle, rle_off,
+                           seq_ascii, qual_ascii, seq_off, has_qual, hp, scratch, scratch_capacity, fd, file_offset);
 }
 
 }  // extern "C"

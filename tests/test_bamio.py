@@ -91,6 +91,14 @@ def test_native_reader_matches_python_reader(golden, tmp_path):
         words, off = cigars_to_rle_batch(kept)
         blob = bamio.format_sam(nb, sel, g, words, off, n_threads=2).tobytes().decode()
         assert blob == "".join(sam_record(w, c) + "\n" for w, c in zip(want, kept))
+        # npore_sam_format_fd: the same block, appended to a file by the formatter threads themselves
+        outp = str(tmp_path / "fd.sam")
+        with open(outp, "wb") as fh:
+            fh.write(b"@HD\n")
+        fd = os.open(outp, os.O_WRONLY)
+        got = bamio.format_sam(nb, sel, g, words, off, n_threads=3, fd=fd, offset=4)
+        os.close(fd)
+        assert open(outp, "rb").read() == b"@HD\n" + blob.encode() and len(got) == len(blob)
         assert len(list(bamio.select_reads(nb, max_reads=1))[0][1]) == 1
         # streaming: small windows (records straddle BGZF members and window ends) deliver the same records in order
         st = bamio.NativeBam(path, n_threads=2, window_bytes=120)

@@ -11,8 +11,8 @@ ref, reads = bench.make_workload(20260101, 1_000_000, n, 10000, NP)
 bench.write_fixture_bam("/tmp/c2.bam", ref, reads)
 fa = {"chr1": ref}
 quick = os.environ.get("NPORE_SWEEP_QUICK")
-for nin in (2, 3):
-    for win in ((8 << 20, 12 << 20, 16 << 20, 24 << 20) if quick else (0, 8 << 20, 16 << 20, 32 << 20)):
+for nin in ((int(x) for x in os.environ["NPORE_SWEEP_INFLIGHT"].split(",")) if os.environ.get("NPORE_SWEEP_INFLIGHT") else (2, 3)):
+    for win in ((4 << 20, 6 << 20, 8 << 20, 12 << 20, 16 << 20) if quick else (0, 8 << 20, 16 << 20, 32 << 20)):
         for mbo in ((64_000_000,) if quick else (8_000_000, 16_000_000, 32_000_000, 64_000_000)):
             best, ph = 1e9, None
             for rep in range(4):
