@@ -86,7 +86,8 @@ int64_t  npore_sam_format(int64_t n, int n_threads,
 /* npore_sam_format + the append to the output file (the `print(..., file=fh)` of src/bam.pyx:81-84) in one pass: every formatter
  * thread pwrite()s its finished slice of records to `fd` at file_offset + (its offset inside the block) while the others still
  * format -- the copy into the page cache runs on all threads and overlaps the formatting.  `scratch` (>= npore_sam_bound bytes)
- * holds the text meanwhile.  Returns the number of bytes appended; the caller advances its end-of-file offset by it. */
+ * holds the text meanwhile.  Returns the number of bytes appended; the caller advances its end-of-file offset by it.  `fd` must
+ * not be in O_APPEND mode (Linux then ignores the offset of pwrite). */
 int64_t  npore_sam_format_fd(int64_t n, int n_threads,
                              const uint8_t *names, const int64_t *name_off, const int32_t *flag, const int32_t *ref_id,
                              const uint8_t *ref_names, const int64_t *ref_name_off, int32_t n_refs,

@@ -323,9 +323,10 @@ def _read_loads(bam, sel, max_b_rows=20000, r=30):
     return (ops + -(-ops // (max_b_rows - 1))) * (2 * r + 1)
 
 
-def _realign_segments(bam, segments, fa, pipe, fh, tm, n_threads, max_batch_ops, n_inflight):
+def _realign_segments(bam, segments, fa, pipe, fd, tm, n_threads, max_batch_ops, n_inflight):
     """The three-stage pipeline over an explicit list of (contig, record indices) segments: gather batch k+1 while batch k is
-    on the GPU and batch k-1 is formatted and written to `fh` -- records in segment order.  Returns the records written."""
+    on the GPU and batch k-1 is formatted and appended to the file descriptor `fd` (not in append mode) -- records in segment
+    order.  Returns the records written."""
     import queue
     import threading
     import time
@@ -334,7 +335,7 @@ def _realign_segments(bam, segments, fa, pipe, fh, tm, n_threads, max_batch_ops,
     from .engine import NPORE_OUT_NO_EXPANDED, NPORE_OUT_RLE, NPORE_OUT_STANDARDIZE, PackedBatch
     flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED
     pending = queue.Queue(maxsize=n_inflight + 1)
-    state = {"written": 0, "error": None}
+    state = {"written": 0, "error": None, "end": os.fstat(fd).st_size}
 
     def retire_loop():
         while True:
@@ -349,9 +350,7 @@ def _realign_segments(bam, segments, fa, pipe, fh, tm, n_threads, max_batch_ops,
                 res, _ = fut.result()
                 t2 = time.perf_counter()
                 _report(res.status[:n], "realign_read")
-                fh.flush()
-                end = os.fstat(fh.fileno()).st_size
-                format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols, fd=fh.fileno(), offset=end)
+                state["end"] += len(format_sam(bam, None, g, res.rle, res.rle_off[:n + 1], n_threads, cols=cols, fd=fd, offset=state["end"]))
                 t3 = time.perf_counter()
                 tm["gpu_wait"] += t2 - t1; tm["format"] += t3 - t2; tm["write"] += time.perf_counter() - t3
                 state["written"] += n
@@ -440,9 +439,14 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
         t1 = time.perf_counter()
         try:
             pipe = _pipeline(sub, npt, n_inflight, devices[g])
-            with open(parts[g], "ab" if g == 0 else "wb") as fh:
-                n = _realign_segments(bam, shard_segs[g], fa, pipe, fh, thread_tm[g], max(1, (n_threads or os.cpu_count() or 1) // G),
+            # (no O_APPEND: Linux ignores the offset of a pwrite on an append-mode descriptor, and the formatter threads place
+            # their slices by offset)
+            fd = os.open(parts[g], os.O_WRONLY | (0 if g == 0 else os.O_CREAT | os.O_TRUNC), 0o644)
+            try:
+                n = _realign_segments(bam, shard_segs[g], fa, pipe, fd, thread_tm[g], max(1, (n_threads or os.cpu_count() or 1) // G),
                                       max_batch_ops, n_inflight)
+            finally:
+                os.close(fd)
             results[g] = (n, time.perf_counter() - t1, None)
         except Exception as e:      # noqa: BLE001
             results[g] = (0, time.perf_counter() - t1, e)
