@@ -412,15 +412,14 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
             }
 
             float Sv[CPL], Sb[CPL], Lv[CPL], Lb[CPL]; uint32_t Sr[CPL], Lr[CPL];     // runs << 16
-            uint32_t any1 = 0u, anyl = 0u, anyg = 0u;
-            bool pl[CPL], pg[CPL];
+            uint32_t any1 = 0u, anyl = 0u, anyg = 0u, gN = 0u;
+            uint32_t lwm[CPL];      // LEN eligibility as data words, not predicates: they stay live across the votes below, and ptxas
+                                    // packs live predicates into a register bit by bit (that was 12 instructions per anti-diagonal)
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 Sv[k] = infd; Lv[k] = infd; Sb[k] = __uint_as_float(FWD_INF_BITS); Lb[k] = __uint_as_float(FWD_INF_BITS); Sr[k] = 0u; Lr[k] = 0u;
-                const uint32_t lw = rw[k] & cb[k].w & 0x03f00000u;          // one-hot LEN period vs the row's "tract present" bits
-                pl[k] = in[k] && lw != 0u;
-                pg[k] = in[k] && (cb[k].z & 1u) != 0u;
-                any1 |= ca[k].w ^ empty_A; anyl |= lw; anyg |= cb[k].z;          // (votes on the unmasked words: slightly conservative)
+                lwm[k] = in[k] ? (rw[k] & cb[k].w & 0x03f00000u) : 0u;    // one-hot LEN period vs the row's "tract present" bits, interior cells only
+                any1 |= ca[k].w ^ empty_A; anyl |= lwm[k]; anyg |= cb[k].z;      // (votes on the unmasked words: slightly conservative)
             }
             // ---- SHR gather: descriptor 0 (largest period), then descriptor 1 if any lane has one
 #pragma unroll
@@ -441,10 +440,10 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
             if (__any_sync(NP_FULL, anyl != 0u)) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
-                    if (pl[k]) {
+                    if (lwm[k] != 0u) {
                         const uint32_t D = cb[k].w;
                         if ((cb[k].z | rw[k]) & 2u) {
-                            pg[k] = true; anyg |= 1u;              // an N inside a k-mer: byte-wise compare on the generic path
+                            gN |= 1u << k; anyg |= 1u;             // an N inside a k-mer: byte-wise compare on the generic path
                         } else {
                             const uint32_t n = D & 7u;
                             // match() of aln.pyx:606-607: seq[i-n .. i) against ref[j .. j+n).  The row record carries the 6-mer
@@ -468,7 +467,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
             if (__any_sync(NP_FULL, (anyg & 1u) != 0u)) {
 #pragma unroll
                 for (int k = 0; k < CPL; k++) {
-                    if (pg[k]) {
+                    if (in[k] && ((cb[k].z | (gN >> k)) & 1u) != 0u) {
                         const int bcn = (int)(((es[k] >> SH) + 1u) & (uint32_t)(NC - 1));
                         const int i = Id + r - bcn, j = Dd - r + bcn;
                         const uint2 rb = rel[j];
