@@ -24,7 +24,8 @@
 //        B ceil(65536 / n)         C 0 if the source column starts the tract, else 0xffff0000
 //        "no candidate": A = the index of the +INF table row, B = C = 0
 //     Z   = [0] generic path (more than two SHR candidates or more than one LEN-eligible period; then S0/S1/LEN are empty)
-//           [1] k-mer contains N  [2:4] base ref[j-1]  [8:19] 2-bit k-mer ref[j..j+5]
+//           [1] k-mer contains N  [2:4] base ref[j-1]  [8:19] 2-bit codes of the LEN unit ref[j..j+n) in the TOP 2n bits of the field
+//           (aligned with the last n codes of rowrec's 6-mer; zero below)  [20:31] the mask of those 2n bits (field position + 12)
 //     LEN = descriptor of the single LEN-eligible period at j: [0:2] n  [3:12] table row  [20:25] one-hot period mask
 //           aligned with rowrec's "tract present" bits (bit 19+n)
 //   rowrec[i] (uint32): [1] k-mer contains N  [5:7] base seq[i-1]  [8:19] 2-bit k-mer seq[i-6..i-1] (the LEN unit
@@ -266,7 +267,13 @@ __global__ void __launch_bounds__(ANN_THREADS) annotate_kernel(AnnotateArgs a)
                 const uint32_t km = kmer2_of(s, len, j, hasN);
                 const bool more = nshr > 2 || nlen > 1;
                 if (more) { sA[0] = sA[1] = empty; sB[0] = sB[1] = sC[0] = sC[1] = 0u; lenw = 0u; }
-                z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (km << 8);
+                uint32_t kf = km, kmask = 0u;
+                if (lenw) {      // the LEN unit ref[j..j+n) moved to the top 2n bits of the k-mer field, where the row's unit seq[i-n..i) sits
+                    const int n = (int)(lenw & 7u);
+                    kmask = ((1u << (2 * n)) - 1u) << (12 - 2 * n);
+                    kf = (km << (12 - 2 * n)) & kmask;
+                }
+                z = (more ? 1u : 0u) | (hasN << 1) | ((base & 7u) << 2) | (kf << 8) | (kmask << 20);
             }
             out[2 * j] = make_uint4(sA[0], sB[0], sC[0], sA[1]);
             out[2 * j + 1] = make_uint4(sB[1], sC[1], z, lenw);

@@ -147,6 +147,7 @@ __device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uin
     Sv = better ? cand : Sv; Sb = better ? base : Sb; Sr = better ? nr : Sr;
 }
 
+__device__ __forceinline__ uint32_t set_lt(float a, float b) { uint32_t m; asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b)); return m; }
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
@@ -447,11 +448,11 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
                         } else {
                             const uint32_t n = D & 7u;
                             // match() of aln.pyx:606-607: seq[i-n .. i) against ref[j .. j+n).  The row record carries the 6-mer
-                            // that ENDS at seq[i-1] (its last n codes are the read-side unit), the column record the 6-mer that
-                            // starts at ref[j]
-                            bool ok = (((((rw[k] >> (12 - 2 * n)) ^ cb[k].z) >> 8) << (32 - 2 * n)) == 0u);
+                            // that ENDS at seq[i-1] (its last n codes = the top 2n bits of the field are the read-side unit), the
+                            // column record ref[j .. j+n) already moved to those bits, and their mask 12 bits higher (annotate.cuh)
+                            bool ok = ((rw[k] ^ cb[k].z) & (cb[k].z >> 12) & 0xfff00u) == 0u;
                             if (!STEADY) ok = ok && (bc[k] + (int)n - (int)((sip >> (4 * n)) & 7u) <= 2 * r - 1);
-                            const bool start = ((rw[k] >> (25 + n)) & 1u) != 0u;
+                            const bool start = (rw[k] & (lwm[k] << 6)) != 0u;                      // "tract start" bit 25+n = the eligible "present" bit 19+n << 6
                             const uint32_t ad = ((dsh - n * ROWB + mypos[k]) & (RING_BYTES - 16u)) | wbase;
                             const float base = lds_f(ad + (start ? 0u : 4u));                       // MAT.VAL or the carried LEN run-start value
                             const uint32_t run0 = start ? 0u : (lds_u_off<12>(ad) & 0xffffu);
@@ -516,17 +517,17 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
             for (int k = 0; k < CPL; k++) {
                 // INS from top = own previous value; DEL from left.  Only the "extended" bits are kept (see common.cuh)
                 const float iv1 = Mv1[k] + gopen, iv2 = Iv1[k] + gext;
-                bool iext = iv2 < iv1;                                               // aln.pyx:536
+                uint32_t iext = set_lt(iv2, iv1);                                    // aln.pyx:536 (all ones / 0: one FSET, no predicate)
                 Iv[k] = fminf(iv1, iv2);
                 const float dv1 = lMv[k] + gopen, dv2 = lDv[k] + gext;
-                bool dext = dv2 < dv1;                                               // aln.pyx:558
+                uint32_t dext = set_lt(dv2, dv1);                                    // aln.pyx:558
                 Dv[k] = fminf(dv1, dv2);
                 uint32_t pm = __viaddmin_u32(dgr[k], 0x10000u, FWD_SAT16);           // typ MAT = 0
                 float dg = dgv[k] + lds_f(subbase + ((rw[k] | cb[k].z) & 0xfcu));    // sub_scores[seq[i-1]][ref[j-1]] (aln.pyx:575)
                 if (!STEADY) {
                     const int i = Id + r - bc[k], j = Dd - r + bc[k];
-                    if (i <= 1) iext = false;                                        // aln.pyx:537-538 (run restarts), :525-528
-                    if (j <= 1) dext = false;                                        // aln.pyx:559-560, :547-550
+                    if (i <= 1) iext = 0u;                                           // aln.pyx:537-538 (run restarts), :525-528
+                    if (j <= 1) dext = 0u;                                           // aln.pyx:559-560, :547-550
                     if (i == 0) Iv[k] = (float)(100 * (j + 1));
                     if (j == 0) Dv[k] = (float)(100 * (i + 1));
                     if (!(i > 0 && j > 0)) { dg = Dv[k] + 100.f; pm = 0u; }
@@ -538,6 +539,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
                 if (Lv[k] == best) p = ((uint32_t)T_LEN << 29) | (WIDE ? min(Lr[k], FWD_SAT16) : Lr[k]);
                 if (Iv[k] == best) p = (uint32_t)T_INS << 29;
                 if (dg == best) p = pm;
+                p |= (iext & ((uint32_t)NP_REC_IE << 16)) | (dext & ((uint32_t)NP_REC_DE << 16));
                 if (!in[k]) p = 0u;
                 if (WIDE) {      // a LEN / SHR record whose run does not fit the field: the true run goes to the overflow list
                     const uint32_t t3 = p >> 29, full = t3 == (uint32_t)T_LEN ? Lr[k] : Sr[k];
@@ -547,8 +549,6 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
                     }
                 }
                 Mr1[k] = dg == best && in[k] ? pm : 0u;                              // match run of this cell (0 unless TYP == MAT)
-                if (iext && in[k]) p |= NP_REC_IE << 16;
-                if (dext && in[k]) p |= NP_REC_DE << 16;
                 pk[k] = p;
                 // history ring: every slot writes; +INF unless the cell is interior
                 sts_slot(rowad + mypos[k], in[k] ? best : __uint_as_float(FWD_INF_BITS), Lb[k], in[k] ? Sb[k] : __uint_as_float(FWD_INF_BITS),
