@@ -71,6 +71,9 @@ struct ForwardArgs {
 #define FWD_SPIN_NS 256
 #endif
 // words of saved per-lane state per cell: Mv1 Iv1 Dv1 dgv Mr1 dgr cc(8) rw
+#define FWD_IE_BIT 27      // NP_REC_IE / NP_REC_DE in the upper half word of a record
+#define FWD_DE_BIT 28
+static_assert((NP_REC_IE << 16) == (1u << FWD_IE_BIT) && (NP_REC_DE << 16) == (1u << FWD_DE_BIT), "record flag bits");
 #define FWD_RR_WORDS 15
 #define FWD_RR_HDR 32      // uint32 words: d, Id, Dd
 static __host__ __device__ inline size_t fwd_rr_state_words(int cpl) { return (size_t)FWD_RR_HDR + (size_t)FWD_RR_WORDS * cpl * 32 + (size_t)32 * cpl * 32; }
@@ -147,7 +150,6 @@ __device__ __forceinline__ void shr_eval(uint32_t A, uint32_t B, uint32_t C, uin
     Sv = better ? cand : Sv; Sb = better ? base : Sb; Sr = better ? nr : Sr;
 }
 
-__device__ __forceinline__ uint32_t set_lt(float a, float b) { uint32_t m; asm("set.lt.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(a), "f"(b)); return m; }
 __device__ __forceinline__ float fmin3(float a, float b, float c)
 { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
 
@@ -517,10 +519,12 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
             for (int k = 0; k < CPL; k++) {
                 // INS from top = own previous value; DEL from left.  Only the "extended" bits are kept (see common.cuh)
                 const float iv1 = Mv1[k] + gopen, iv2 = Iv1[k] + gext;
-                uint32_t iext = set_lt(iv2, iv1);                                    // aln.pyx:536 (all ones / 0: one FSET, no predicate)
+                // "extended" (aln.pyx:536, 558) = strict '<' = the sign bit of the difference: the operands are finite (MAT / INS / DEL values
+                // are never the ring's +INF), a difference of distinct floats never rounds to zero, and x - x = +0
+                uint32_t iext = __float_as_uint(iv2 - iv1);
                 Iv[k] = fminf(iv1, iv2);
                 const float dv1 = lMv[k] + gopen, dv2 = lDv[k] + gext;
-                uint32_t dext = set_lt(dv2, dv1);                                    // aln.pyx:558
+                uint32_t dext = __float_as_uint(dv2 - dv1);
                 Dv[k] = fminf(dv1, dv2);
                 uint32_t pm = __viaddmin_u32(dgr[k], 0x10000u, FWD_SAT16);           // typ MAT = 0
                 float dg = dgv[k] + lds_f(subbase + ((rw[k] | cb[k].z) & 0xfcu));    // sub_scores[seq[i-1]][ref[j-1]] (aln.pyx:575)
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
                 if (Lv[k] == best) p = ((uint32_t)T_LEN << 29) | (WIDE ? min(Lr[k], FWD_SAT16) : Lr[k]);
                 if (Iv[k] == best) p = (uint32_t)T_INS << 29;
                 if (dg == best) p = pm;
-                p |= (iext & ((uint32_t)NP_REC_IE << 16)) | (dext & ((uint32_t)NP_REC_DE << 16));
+                p |= ((iext >> (31 - FWD_IE_BIT)) & (1u << FWD_IE_BIT)) | ((dext >> (31 - FWD_DE_BIT)) & (1u << FWD_DE_BIT));
                 if (!in[k]) p = 0u;
                 if (WIDE) {      // a LEN / SHR record whose run does not fit the field: the true run goes to the overflow list
                     const uint32_t t3 = p >> 29, full = t3 == (uint32_t)T_LEN ? Lr[k] : Sr[k];
