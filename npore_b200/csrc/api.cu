@@ -172,14 +172,25 @@ int launch_forward(npore_ctx *ctx, const ForwardArgs &fa, int n_sub)
 
 // Which instantiation runs a sub-batch at band slots NC = 32 * nc32: one chunk per warp, or a team of warps per chunk
 // (forward.cuh).  Measured on C4 (profiles/r02_ab_experiments.md): NC = 256 runs fastest as four-warp teams <2,4> (126 registers,
-// 16 warps/SM; <8,1> needs 255), NC = 128 as two-warp teams <2,2>; NC = 64 as one warp per chunk unless the launch cannot fill
-// the warp slots -- judged by its effective parallelism par = (sum of chunk lengths) / (longest chunk), which is what bounds a
-// launch whose chunks never wait for a warp.  Alone on the device: teams when par <= 2/3 of the slots (C1, 50 k-row windows; the
-// two forms are within 5% of each other around the threshold).  Beside other contexts (live on the device, or `others` = the par
-// of their launches in flight: PipelinedRealigner, the file pipeline) the one-warp form is the better neighbour -- a 1,000-read batch takes 14.2 instead of
-// 13.6 ms but leaves 60% of the warp slots to the next batch instead of 20% -- so teams only while everything in flight together
-// is below a quarter of the slots.  NPORE_TEAM=1/2/4 forces the choice (tests, A/B).
-inline int forward_team(const npore_ctx *ctx, int nc32, double par, double others)
+// 16 warps/SM; <8,1> needs 255), NC = 128 as two-warp teams <2,2>.  NC = 64: one warp per chunk unless the launch cannot fill the
+// warp slots.  A launch whose chunks never wait for a warp takes (longest chunk) x (time per anti-diagonal at that occupancy); one
+// whose chunks queue takes (sum of chunk lengths) x (time per anti-diagonal at full occupancy) / slots.  Both forms are estimated
+// from the measured per-anti-diagonal times below (profiles/r02_batch_size_sweep.md: us per anti-diagonal of a chunk vs the share
+// of the warp slots in use) with par = (sum of chunk lengths) / (longest chunk), and the faster one is taken: teams for C1, for
+// batches below ~900 reads, for 50 k-row windows (1,801 chunks of very different lengths); one warp for C5's 1,600 equal chunks.
+// Beside other contexts (live on the device, or `others` = the par of their launches in flight: PipelinedRealigner, the file
+// pipeline) the one-warp form is the better neighbour -- a 1,000-read batch leaves 60% of the warp slots to the next batch
+// instead of 20% -- so teams only while everything in flight together is below a quarter of the slots.
+// NPORE_TEAM=1/2/4 forces the choice (tests, A/B).
+inline double lerp_tab(const double (*tab)[2], int n, double x)
+{
+    if (x <= tab[0][0]) return tab[0][1];
+    for (int i = 1; i < n; i++)
+        if (x <= tab[i][0]) return tab[i - 1][1] + (tab[i][1] - tab[i - 1][1]) * (x - tab[i - 1][0]) / (tab[i][0] - tab[i - 1][0]);
+    return tab[n - 1][1];
+}
+
+inline int forward_team(const npore_ctx *ctx, int nc32, int n_chunks, double par, double others)
 {
     if (nc32 == 1) return 1;
     if (const char *e = getenv("NPORE_TEAM")) { const int t = atoi(e); if (t == 1 || t == 2) return t; if (t == 4) return nc32 == 8 ? 4 : 2; }
@@ -188,7 +199,12 @@ inline int forward_team(const npore_ctx *ctx, int nc32, double par, double other
     const double slots = ctx->sm_count * 16.0;          // resident one-warp chunks of <2,1>
     const bool siblings = ctx->device < 64 && g_ctx_on_device[ctx->device].load() > 1;      // a pipeline: the next batch is on its way
     if (others > 0.0 || siblings) return 4.0 * (par + others) <= slots ? 2 : 1;
-    return 3.0 * par <= 2.0 * slots ? 2 : 1;
+    // us per anti-diagonal of one chunk (r = 30, 10 kb reads) against the share of the warp slots the launch occupies
+    static const double S1[][2] = {{0.04, 0.536}, {0.10, 0.559}, {0.21, 0.582}, {0.32, 0.635}, {0.42, 0.652}, {0.63, 0.750}, {0.84, 0.897}, {1.0, 0.93}};
+    static const double S2[][2] = {{0.08, 0.458}, {0.21, 0.476}, {0.42, 0.537}, {0.63, 0.588}, {0.84, 0.663}, {1.0, 0.80}};
+    const double t1 = std::max(lerp_tab(S1, 8, std::min(1.0, n_chunks / slots)), par * 0.93 / slots);
+    const double t2 = std::max(lerp_tab(S2, 6, std::min(1.0, 2.0 * n_chunks / slots)), par * 0.60 / (0.5 * slots));
+    return t2 < t1 ? 2 : 1;
 }
 
 // BAM 4-bit bases -> base codes (cig.pyx:212-229 on the device): grid (items, parts)
@@ -581,7 +597,7 @@ static int run_pass(npore_ctx *ctx, uint32_t flags, bool wide, int *n_sat)
         for (int k = 0; k < sb.count; k++) { const int b = ctx->chunk_bmax[ctx->order[sb.first + k]]; bm = std::max(bm, b); bsum += b; }
         const long long par = (long long)(bsum / bm) + 1;
         const long long others = inflight.set(par);                  // the other contexts' launches on this device
-        const int team = forward_team(ctx, ctx->cpl, (double)par, (double)others);      // warps per chunk of this sub-batch's forward launch
+        const int team = forward_team(ctx, ctx->cpl, sb.count, (double)par, (double)others);      // warps per chunk of this sub-batch's forward launch
         aa.cpl = ctx->cpl / team;
         CU(cudaEventRecord(e0, ctx->stream));
         {   // equality words of all periods in dynamic shared memory: 6 planes of (longest slice / 32 + 2) words
