@@ -539,8 +539,21 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
     fa = read_fasta(fasta) if isinstance(fasta, str) else fasta
     # several regions are served region by region (bam.pyx:27-28), which needs the whole file at hand
     bam = NativeBam(bam_fn, n_threads, window_bytes=window_bytes if not (regions and len(regions) > 1) else 0)
+    mark("bam open")
     streaming = bam.window_bytes > 0
-    create_header(f"{cfg.args.out_prefix}.sam", bam.refs, argv)
+    # the header (and the truncation of a previous output: ~2 ms for a 60 MB file) is written beside the first window's inflate;
+    # the writer thread waits for it before it opens the file
+    header_err = []
+
+    def write_header():
+        try:
+            create_header(f"{cfg.args.out_prefix}.sam", bam.refs, argv)
+            mark("header written")
+        except Exception as e:      # noqa: BLE001
+            header_err.append(e)
+
+    header = threading.Thread(target=write_header, daemon=True)
+    header.start()
     sub, npt = _tables()
     pipe = _pipeline(sub, npt, n_inflight, devices[0] if devices else None)
     flags = NPORE_OUT_STANDARDIZE | NPORE_OUT_RLE | NPORE_OUT_NO_EXPANDED
@@ -552,12 +565,16 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
 
     def retire_loop():
         path = f"{cfg.args.out_prefix}.sam"
-        fd = os.open(path, os.O_WRONLY)
-        end = os.path.getsize(path)                       # the header is there already
+        header.join()
+        if header_err:
+            state["error"] = header_err[0]
+        fd = os.open(path, os.O_WRONLY) if not header_err else -1
+        end = os.path.getsize(path) if fd >= 0 else 0     # the header is there already
         while True:
             item = pending.get()
             if item is None:
-                os.close(fd)
+                if fd >= 0:
+                    os.close(fd)
                 return
             if state["error"] is not None:
                 continue                              # keep draining so that the producer never blocks
@@ -582,6 +599,9 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
 
     retire = threading.Thread(target=retire_loop, daemon=True)
     retire.start()
+    # the text gather runs right after a submit: leave cores to the GPU worker thread that has just been woken (on 16 cores a
+    # 16-thread gather delayed the start of the upload by 2 ms) and to the writer
+    nt_text = max(1, (n_threads or os.cpu_count() or 1) - int(os.environ.get("NPORE_SPARE_CORES", "3")))
     try:
         kept = 0
         while True:
@@ -611,7 +631,7 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
                                                               nib, nib_start, bam.aln_len[part], cig_words, cig_off)
                     fut = pipe.submit(packed, flags)                          # the GPU starts; the SAM-text gather runs beside it
                     mark(f"submitted n={len(part)}")
-                    g = bam.gather(part, n_threads, want_codes=False, want_cigar=False)  # ASCII bases / qualities / names
+                    g = bam.gather(part, nt_text, want_codes=False, want_cigar=False)    # ASCII bases / qualities / names
                     mark("text gathered")
                     item = (fut, take_columns(bam, part), g, len(part))
                     tm["gather"] += time.perf_counter() - t1
