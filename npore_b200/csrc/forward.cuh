@@ -232,18 +232,23 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
 
     for (;;) {
         int idx = 0;
-        {   // pop the next runnable chunk (FIFO); wait for a push if the queue is momentarily empty
+        {   // pop the next runnable chunk (FIFO).  An empty queue stays empty -- a chunk is handed back only while another one
+            // waits (tail - head > 0 at its slice boundary), and a finished chunk takes one out -- so a warp (team) that finds
+            // nothing queued is done and leaves: idle pollers would take issue slots from the warps still working on the tail.
+            // Only a warp that saw an entry and lost the race for it waits (for a hand-back, or for the end of the launch).
             if (lane == 0 && wt == 0) {
-                const int pos = atomicAdd(a.rr_ctl, 1);
-                int *qp = a.rr_q + (pos & a.rr_mask);
-                int v;
-                unsigned ns = FWD_SPIN_NS;
-                while ((v = ld_cg_poll(qp)) < 0) {
-                    if (ld_cg_poll(a.rr_ctl + 2) >= a.n) { v = -2; break; }
-                    __nanosleep(ns);
-                    if (ns < 4096u) ns <<= 1;
+                int v = -2;
+                if (ld_cg_poll(a.rr_ctl + 1) - ld_cg_poll(a.rr_ctl) > 0) {
+                    const int pos = atomicAdd(a.rr_ctl, 1);
+                    int *qp = a.rr_q + (pos & a.rr_mask);
+                    unsigned ns = FWD_SPIN_NS;
+                    while ((v = ld_cg_poll(qp)) < 0) {
+                        if (ld_cg_poll(a.rr_ctl + 2) >= a.n) { v = -2; break; }
+                        __nanosleep(ns);
+                        if (ns < 4096u) ns <<= 1;
+                    }
+                    if (v >= 0) __stcg(qp, -1);
                 }
-                if (v >= 0) __stcg(qp, -1);
                 idx = v;
             }
             if (T > 1) {      // the team's first warp popped: hand the index to the others
