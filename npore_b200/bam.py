@@ -62,12 +62,12 @@ def realign_read(read_data):
 def realign_haps(hap_data, max_batch_ops=300_000_000):
     """bam.pyx:93-123 for a list of (contig, hap, seq, ref, expanded_cigar) -> same tuples with the standardised
     expanded CIGAR (over 'MID')."""
-    sub, npt = _tables()
-    eng = _engine(sub, npt, 5, 1, 20000, 30)
-    out = []
     hap_data = list(hap_data)
     from .engine import check_item_sizes
     check_item_sizes([len(h[3]) for h in hap_data], [len(h[2]) for h in hap_data], what="haplotype")     # per item, before any batch runs
+    sub, npt = _tables()
+    eng = _engine(sub, npt, 5, 1, 20000, 30)
+    out = []
     for batch in iter_batches(hap_data, lambda h: len(h[2]) + len(h[3]), max_batch_ops):
         packed = PackedBatch.from_strings([h[3] for h in batch], [h[2] for h in batch], [h[4] for h in batch])
         res = eng.align_packed(packed, NPORE_OUT_STANDARDIZE, eng.new_result(packed, NPORE_OUT_STANDARDIZE, pinned=False))

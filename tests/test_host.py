@@ -172,3 +172,17 @@ def test_batch_codecs_match_single_item_codecs():
         assert getattr(p, f).tolist() == getattr(q, f).tolist()
     assert p.ref_codes[:p.ref_total].tolist() == q.ref_codes[:q.ref_total].tolist()
     assert p.cigar_rle[:4].tolist() == q.cigar_rle[:4].tolist() and p.total_ops == q.total_ops
+
+
+def test_oversize_item_is_reported_per_item_before_any_batch(monkeypatch):
+    """one item with ref_len + seq_len >= 2^28 used to fail the whole npore_upload with NPORE_ERR_BAD_ARG,
+    valid items included.  The size is checked per item, with the item named, before anything is sent to the device."""
+    from npore_b200 import bam, engine
+    engine.check_item_sizes([1 << 27], [(1 << 27) - 1])                       # exactly at the limit: accepted
+    with pytest.raises(engine.NporeError, match=r"item 1: ref_len \+ seq_len = 268435456 exceeds"):
+        engine.check_item_sizes([10, 1 << 27], [10, 1 << 27])
+    monkeypatch.setattr(engine, "MAX_ITEM_OPS", 20)                           # realign_haps: checked before an engine exists
+    haps = [("c", 1, "ACGT", "ACGT", "===="), ("c", 2, "ACGTACGTACGT", "ACGTACGTACGT", "=" * 12)]
+    with pytest.raises(engine.NporeError, match=r"haplotype 1: ref_len \+ seq_len = 24 exceeds"):
+        bam.realign_haps(haps)
+

@@ -59,6 +59,18 @@ for r, mb in ((30, 20000), (60, 5000), (100, 20000)):
     want = oracle.standardize(oracle.align(ir, iq, cig.expand_cigar(rd[5]), S, NP, max_b_rows=mb, r=r), ir, iq)
     bad += (o[0] != want) + (c[0] != oracle.collapse_cigar(want))
     eng.close()
+# time-sliced teams: more chunks than resident teams, 24-step slices -- state save / restore, mailbox rebuild, team barriers
+rs = synth.make_reads(ref, 100, 1200, rng, cm, tracts=tr)
+os.environ["NPORE_RR_SLICE"] = "24"
+for team, r, mb in (("2", 30, 48), ("4", 100, 120)):
+    os.environ["NPORE_TEAM"] = team
+    eng = Realigner(S, NP, max_b_rows=mb, r=r)
+    irs, iqs, cgs = [oracle.bases_to_int(x[9]) for x in rs], [oracle.bases_to_int(x[7]) for x in rs], [cig.expand_cigar(x[5]) for x in rs]
+    outs, _, _ = eng.align_many(irs, iqs, cgs)
+    bad += sum(o != oracle.align(a_r, a_q, cg, S, NP, max_b_rows=mb, r=r) for o, a_r, a_q, cg in zip(outs, irs, iqs, cgs))
+    eng.close()
+os.environ.pop("NPORE_TEAM", None)
+os.environ["NPORE_RR_SLICE"] = "40"
 # confusion matrices
 import pileup_oracle as po
 from npore_b200 import confusion
