@@ -327,7 +327,11 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
             for (int t = wt; t < NC / 4; t += T)
                 asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%2};" :: "r"(wbase + (uint32_t)(t * 32 + lane) * 16u), "r"(FWD_INF_BITS), "r"(0u) : "memory");
         }
-        {   // prime the column-record FIFO: records [cn, (cn & ~15) + 32), cn = the next column to enter the band
+        {   // prime the column-record FIFO: records [cn, (cn & ~15) + 32), cn = the next column to enter the band.  The previous
+            // chunk's last refill may still be in flight (nothing waited for it if the chunk ended or was handed back first) and
+            // would land on top of the new records: drain it before the slots are written again (racecheck found this WAW)
+            cp_async_wait_all();
+            __syncwarp();
             const int cn = Dd - r + NC + 1, lim = (cn & ~15) + 32;
 #pragma unroll
             for (int t = 0; t < 2; t++) {
