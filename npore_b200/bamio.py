@@ -653,8 +653,8 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
 
 
 # ------------------------------------------------------------------------------------------------ minimal BAM writer
-def _bgzf_block(payload: bytes) -> bytes:
-    comp = zlib.compressobj(6, zlib.DEFLATED, -15)
+def _bgzf_block(payload: bytes, level: int = 6) -> bytes:
+    comp = zlib.compressobj(level, zlib.DEFLATED, -15)
     cdata = comp.compress(payload) + comp.flush()
     bsize = len(cdata) + 25
     return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + cdata +
@@ -669,9 +669,12 @@ def _reg2bin(beg, end):
     return 0
 
 
-def write_bam(path, header_text, refs, records):
+def write_bam(path, header_text, refs, records, level=6):
     """records: dicts with name, flag, ref_id, pos, mapq, cigar (list of (len, op_char)), seq, qual (bytes/None), tags
-    ({'HP': int} supported)."""
+    ({'HP': int} supported).  level: zlib level of the BGZF members."""
+    lut = np.full(256, 15, np.uint8)
+    for i, c in enumerate(_SEQ16):
+        lut[ord(c)] = i
     out = io.BytesIO()
     text = header_text.encode()
     out.write(b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(refs)))
@@ -680,8 +683,9 @@ def write_bam(path, header_text, refs, records):
     for r in records:
         cig = [(n << 4) | _OPS.index(op) for n, op in r["cigar"]]
         seq = r["seq"]
-        codes = [_SEQ16.index(c) if c in _SEQ16 else 15 for c in seq] + [0]
-        packed = bytes((codes[i] << 4) | codes[i + 1] for i in range(0, len(seq), 2))
+        codes = np.zeros(len(seq) + (len(seq) & 1), np.uint8)
+        codes[:len(seq)] = lut[np.frombuffer(seq.encode("latin-1"), np.uint8)]
+        packed = ((codes[0::2] << 4) | codes[1::2]).tobytes()
         qual = bytes([0xFF] * len(seq)) if r.get("qual") is None else bytes(r["qual"])
         tags = b"".join(b"HPi" + struct.pack("<i", v) if k == "HP" else b"" for k, v in r.get("tags", {}).items())
         span = sum(n for n, op in r["cigar"] if op in "MDN=X") or 1
@@ -693,5 +697,5 @@ def write_bam(path, header_text, refs, records):
     raw = out.getvalue()
     with open(path, "wb") as fh:
         for i in range(0, len(raw), 60000):
-            fh.write(_bgzf_block(raw[i:i + 60000]))
+            fh.write(_bgzf_block(raw[i:i + 60000], level))
         fh.write(_bgzf_block(b""))
