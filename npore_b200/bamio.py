@@ -395,7 +395,6 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
     data-path collective); the host gathers the per-region SAM bodies in region order into ONE file, byte-identical to the
     single-GPU output.  `devices` may name a device more than once (several pipelines on one GPU).  timings: per phase, summed
     over the shards, plus 'shards': [{device, reads, cell_updates, seconds}] and 'concat' seconds."""
-    import shutil
     import threading
     import time
     from .bam import _tables
@@ -463,11 +462,29 @@ def realign_bam_sharded(bam_fn, fasta, devices, out_prefix=None, regions=None, m
         if err is not None:
             raise err
     t2 = time.perf_counter()
-    with open(out, "ab") as fh:                                     # host gather: region order = coordinate order
+    dst = os.open(out, os.O_WRONLY)                                 # host gather: region order = coordinate order
+    try:
+        end = os.fstat(dst).st_size
         for g in range(1, G):
             with open(parts[g], "rb") as src:
-                shutil.copyfileobj(src, fh, 16 << 20)
+                left = os.fstat(src.fileno()).st_size
+                try:                                                # in-kernel copy (no bounce through user space)
+                    while left > 0:
+                        n = os.copy_file_range(src.fileno(), dst, left, None, end)
+                        if n <= 0:
+                            break
+                        left -= n; end += n
+                except (AttributeError, OSError):
+                    pass
+                while left > 0:                                     # not supported here (or stopped early): plain copy of the rest
+                    buf = os.pread(src.fileno(), min(left, 16 << 20), os.fstat(src.fileno()).st_size - left)
+                    if not buf:
+                        raise OSError(f"short read while gathering {parts[g]}")
+                    os.pwrite(dst, buf, end)
+                    left -= len(buf); end += len(buf)
             os.remove(parts[g])
+    finally:
+        os.close(dst)
     tm["concat"] += time.perf_counter() - t2
     for k in ("gather", "gpu_wait", "format", "write"):
         tm[k] += sum(x[k] for x in thread_tm)
