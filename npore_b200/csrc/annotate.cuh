@@ -32,8 +32,6 @@
 //                       seq[i-n..i) is its last n codes)
 //                       [20:25] tract present at i-n (bit 19+n)  [26:31] tract start at i-n (bit 25+n, L_IDX==0)
 #pragma once
-#include <type_traits>
-
 #include "common.cuh"
 
 #define ANN_THREADS 256
@@ -85,9 +83,7 @@ __device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n
         if (tid < NP_MAXN) { e6[tid * e6_stride + nwords] = 0u; e6[tid * e6_stride + nwords + 1] = 0u; }
     }
     __syncthreads();
-    // one instantiation per period: the bit tricks and the divisions by n below fold to constants (a run-time n cost ~20 % of the kernel)
-    auto period = [&](auto n_tag) {
-        constexpr int n = decltype(n_tag)::value;
+    for (int n = 1; n <= max_n; n++) {
         uint32_t *s_e = ebits_long ? ebits_long : all_periods ? e6 + (n - 1) * e6_stride : s_e_smem;      // long stand-alone sequences: global memory
         if (!all_periods) {
             for (int base = (tid >> 5) << 5; base < nwords * 32; base += ANN_THREADS) {
@@ -186,14 +182,7 @@ __device__ void annotate_slice(const uint8_t *__restrict__ s, int len, int max_n
             }
         }
         __syncthreads();
-    };
-    if (max_n >= 1) period(std::integral_constant<int, 1>{});
-    if (max_n >= 2) period(std::integral_constant<int, 2>{});
-    if (max_n >= 3) period(std::integral_constant<int, 3>{});
-    if (max_n >= 4) period(std::integral_constant<int, 4>{});
-    if (max_n >= 5) period(std::integral_constant<int, 5>{});
-    if (max_n >= 6) period(std::integral_constant<int, 6>{});
-    static_assert(NP_MAXN == 6, "one call per period above");
+    }
 }
 
 __device__ __forceinline__ uint32_t raw_byte(const uint8_t *raw, int len, int p, int n)

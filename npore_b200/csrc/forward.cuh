@@ -330,8 +330,10 @@ __global__ void __launch_bounds__(fwd_warps(CPL, T) * 32, T == 4 ? 2 : CPL <= 2 
         {   // prime the column-record FIFO: records [cn, (cn & ~15) + 32), cn = the next column to enter the band.  The previous
             // chunk's last refill may still be in flight (nothing waited for it if the chunk ended or was handed back first) and
             // would land on top of the new records: drain it before the slots are written again (racecheck found this WAW)
+#ifndef FWD_NO_PRIME_DRAIN      // (A/B switch)
             cp_async_wait_all();
             __syncwarp();
+#endif
             const int cn = Dd - r + NC + 1, lim = (cn & ~15) + 32;
 #pragma unroll
             for (int t = 0; t < 2; t++) {

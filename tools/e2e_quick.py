@@ -19,5 +19,6 @@ for rep in range(reps + 2):
     bamio.realign_bam("/tmp/c2.bam", fa, out_prefix="/tmp/c2_out", argv=["x"], timings=tm)
     ts.append(time.perf_counter() - t)
 ts = np.array(ts[2:])
+print("all calls (ms):", " ".join(f"{1e3 * t:.1f}" for t in ts))
 print(f"{n} reads: best {1e3 * ts.min():.1f} ms = {n / ts.min():.0f} reads/s, median {1e3 * np.median(ts):.1f} ms = {n / np.median(ts):.0f} reads/s  " +
       " ".join(f"{k} {1e3 * v:.0f}" for k, v in tm.items() if isinstance(v, float)))
