@@ -1,6 +1,6 @@
 // forward.cuh -- the align() recurrence (reference: src/aln.pyx:465-667) as an anti-diagonal wavefront.  Round-2 form.
 //
-// One warp owns one chunk at a time (persistent warps, round-robin run queue).  Lane layout is COLUMN-STATIONARY: physical
+// One warp (or team of warps, below) owns one chunk at a time (persistent warps, round-robin run queue).  Lane layout is COLUMN-STATIONARY: physical
 // slot s = (column index j) mod NC, NC = 32*CPL >= W = 2r+1, lane l holds slots l*CPL .. l*CPL+CPL-1 in registers (CPL = 2
 // at the default r = 30).  The band of anti-diagonal d is the window of columns [jlo, jlo+NC), jlo = (#D ops so far) - r;
 // b_col = j - jlo.  Consequences:
@@ -22,15 +22,21 @@
 //     (aln.pyx:609-612, 620-622, 645-647, 655-656).  One exception: when NC - W < 4, NC-W+3 equal ops among the last n <= max_n
 //     make slot (j-n) mod NC alias a live cell of another column; 32-step blocks that contain such a window (six equal ops
 //     in a row at r = 30) run the checked variant.  The form is validated on the CPU by oracle/pull_model.c:pm2_align.
-//   * score tables re-laid per (n, L): tabS[row][q] = np_score(n, L, -(q+1)), tabL[row][q] = np_score(n, L, q+1)
-//     (aln.pyx:257-274 incl. its clamps and its "ref_l + indel < 0 -> 100"), q = trunc(run/n) clamped to 127 -- beyond that
-//     both are constant.  run/n is one IMAD.HI with a 16-bit reciprocal held in the descriptor (exact below the clamp).
+//   * score tables re-laid per (n, L), q-major: tabS[q][row] = np_score(n, L, -(q+1)), tabL[q][row] = np_score(n, L, q+1)
+//     (aln.pyx:257-274 incl. its clamps and its "ref_l + indel < 0 -> 100"), q = trunc(run/n) < NP_TABQ = 2048 = the saturated
+//     run, so no clamp instruction; row np_rows is all +INF ("no candidate").  run/n is one IMAD.HI with the 17-bit reciprocal
+//     held in the descriptor (exact for runs below 2^16).
 //   * MAT's packed 16-bit record (TYP, RUN, two INDEL 'extended' bits; common.cuh) -- all that traceback reads
 //     (aln.pyx:683-685) -- is streamed to HBM, one coalesced 64*CPL-byte row per anti-diagonal, in slot order.
 //   * the anti-diagonals of a chunk are walked in blocks of <= 32 (one word of the D/I bit string).  A block is STEADY when
 //     every cell 1 <= b_col <= 2r-1 of every step is an interior cell with i, j >= 2 and no aliasing window occurs; steady
 //     blocks run a lean step (constant bounds, no first-row/column code, no source tests), the others the checked step.
-// Arithmetic: fp32 add and strict compare only, tie-break order of aln.pyx:585-592; compiled with --fmad=false.
+//   * forward_kernel<CPL, T>: T = 1 as above; T = 2 / 4 splits the band's NC = 32*CPL*T slots across the warps of a TEAM (team
+//     ring, 16-byte mailbox for the neighbour across the warp border, one named barrier per anti-diagonal) -- for launches that
+//     cannot fill the warp slots and for bands wider than 64 cells (api.cu: forward_team).  Teams are time-sliced like warps.
+//   * flags that stay live across the warp votes of a step are kept as data words (lwm[], gN), not bools: ptxas keeps live
+//     predicates by packing them bit by bit into a register, which cost 12 instructions per anti-diagonal.
+// Arithmetic: fp32 add / subtract and strict compare only, tie-break order of aln.pyx:585-592; compiled with --fmad=false.
 #pragma once
 #include "common.cuh"
 #include <type_traits>
