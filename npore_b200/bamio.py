@@ -507,8 +507,8 @@ def _keep_freed_buffers_mapped():
     CIGAR gathers, SAM text columns, result arrays, the 20 MB SAM blob -- are recycled from the heap instead of being mmap'ed,
     page-faulted by 16 threads at once and munmap'ed again for every window.  Measured on the C2 file (16 host cores): the
     gathers in front of the second and third upload took 8-12 ms instead of 1 ms (page faults + address-space lock beside the
-    inflating prefetch threads), the whole file 67 -> 64 ms with the GPU, not the host, the limiter afterwards
-    (profiles/r02_ab_experiments.md).  NPORE_NO_MALLOPT=1 leaves the allocator alone."""
+    inflating prefetch threads); with it the host is through all windows of the 3,000-read file after 27 ms and the GPU, not
+    the host, limits the call (profiles/r02_ab_experiments.md).  NPORE_NO_MALLOPT=1 leaves the allocator alone."""
     global _MALLOC_TUNED
     if _MALLOC_TUNED or os.environ.get("NPORE_NO_MALLOPT"):
         return
@@ -529,7 +529,8 @@ def realign_bam(bam_fn, fasta, out_prefix=None, regions=None, max_reads=0, argv=
     Flat arrays all the way, as a pipeline: the reader streams the file in windows of ~window_bytes of inflated records
     (native, multi-threaded) and gathers batch k+1 while batch k is on the GPU (n_inflight contexts) and a third thread
     formats (native) and writes batch k-1.  One shared reference slice is uploaded per batch.
-    timings: optional dict that receives host seconds per phase (open, gather, gpu_wait, format, write).
+    timings: optional dict that receives host seconds per phase (open, gather, gpu_wait, format = formatting + the append to the
+    file, write = 0 since the formatter threads write themselves); timings["trace"] = [] collects (seconds, event) of every step.
     devices: CUDA device indices; more than one -> realign_bam_sharded (one region-shard pipeline per device, ordered gather)."""
     if devices is not None and len(devices) > 1:
         return realign_bam_sharded(bam_fn, fasta, list(devices), out_prefix=out_prefix, regions=regions, max_reads=max_reads, argv=argv,
