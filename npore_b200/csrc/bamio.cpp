@@ -396,6 +396,8 @@ int npore_bam_gather(const npore_bam *b, int64_t n_sel, const int64_t *sel, int 
         if (sel[k] < 0 || (size_t)sel[k] >= b->recs.size()) return io_fail(NPORE_IO_ERR_ARG, "record index out of range");
     uint8_t code_of[16];
     for (int c = 0; c < 16; c++) code_of[c] = kNt16[c] == 'A' ? 1 : kNt16[c] == 'C' ? 2 : kNt16[c] == 'G' ? 3 : kNt16[c] == 'T' ? 4 : 0;
+    uint16_t pair_of[256];               // packed byte -> its two letters in memory order (first base = high nibble)
+    for (int v = 0; v < 256; v++) { const uint8_t two[2] = {(uint8_t)kNt16[v >> 4], (uint8_t)kNt16[v & 15]}; std::memcpy(&pair_of[v], two, 2); }
     std::atomic<int> bad{0};
     parallel_for(n_sel, n_threads, [&](int64_t lo, int64_t hi) {
         for (int64_t k = lo; k < hi; k++) {
@@ -408,7 +410,13 @@ int npore_bam_gather(const npore_bam *b, int64_t n_sel, const int64_t *sel, int 
             if (seq_off && seq_off[k + 1] - seq_off[k] != n) { bad = 1; continue; }
             if (cig_off && cig_off[k + 1] - cig_off[k] != r.n_cigar_kept) { bad = 1; continue; }
             if (name_off && name_off[k + 1] - name_off[k] != r.name_len) { bad = 1; continue; }
-            if (seq_ascii || seq_codes) {
+            if (seq_ascii && !seq_codes) {      // the SAM-text gather: two letters per packed byte from a 256-entry table
+                uint8_t *a = seq_ascii + seq_off[k];
+                int t = 0, q = r.lead;
+                if (n > 0 && (q & 1)) { a[t++] = kNt16[sq[q >> 1] & 15]; q++; }
+                for (; t + 1 < n; t += 2, q += 2) std::memcpy(a + t, &pair_of[sq[q >> 1]], 2);
+                if (t < n) a[t] = kNt16[sq[q >> 1] >> 4];
+            } else if (seq_ascii || seq_codes) {
                 uint8_t *a = seq_ascii ? seq_ascii + seq_off[k] : nullptr, *c = seq_codes ? seq_codes + seq_off[k] : nullptr;
                 for (int t = 0; t < n; t++) {
                     const int q = r.lead + t;

@@ -257,6 +257,9 @@ def test_gather_nib_is_the_file_packing(tmp_path):
         b = nib[idx >> 1] if n else np.zeros(0, np.uint8)
         v = np.where(idx & 1, b & 15, b >> 4)
         assert np.array_equal(lut[v], g["seq_codes"][g["seq_off"][k]:g["seq_off"][k + 1]])
+    # the text-only gather (two letters per packed byte; odd and even clip lengths, odd and even read lengths) == the per-base one
+    gt = nb.gather(sel, want_codes=False, want_cigar=False)
+    assert np.array_equal(gt["seq_ascii"][:int(gt["seq_off"][-1])], g["seq_ascii"][:int(g["seq_off"][-1])])
     nb.close()
 
 
