@@ -295,3 +295,28 @@ def test_malformed_inputs_are_rejected_not_read_out_of_bounds(tmp_path):
     with pytest.raises(ValueError):
         bamio.NativeBam(path)
     assert "npore_bam_gather_nib" in _lib.IO_EXPORTS
+
+
+def test_short_last_window_is_merged_and_prefetch_keeps_the_order(tmp_path):
+    """Streaming reader: the window after the current one is inflated in the background (npore_bam_prefetch) and a last window
+    that would hold less than 0.4 windows of records is taken by its predecessor (a short last batch costs a full chunk latency
+    on the GPU).  The records still arrive once each, in file order."""
+    rng = np.random.default_rng(5)
+    recs = [{"name": f"r{k:05d}", "flag": 0, "ref_id": 0, "pos": 3 * k, "mapq": 20, "cigar": [(150, "M")], "seq": "".join(rng.choice(list("ACGT"), size=150)),
+             "qual": bytes([30] * 150), "tags": {"HP": k % 3}} for k in range(1000)]
+    path = str(tmp_path / "w.bam")
+    bamio.write_bam(path, "@HD\tVN:1.6\tSO:coordinate\n", [("a", 10_000)], recs)
+    whole = bamio.NativeBam(path)
+    per_record = 4 + 32 + 7 + 4 + 75 + 150 + 7                     # block_size field + fixed part + name + 1 cigar word + packed bases + quals + HP tag
+    total = per_record * len(recs)
+    window = int(total / 2.25)                                      # naive cut: two full windows and a quarter
+    st = bamio.NativeBam(path, n_threads=2, window_bytes=window)
+    sizes, names = [], []
+    while st.advance():
+        sizes.append(st.n)
+        g = st.gather(np.arange(st.n), want_codes=False, want_cigar=False)
+        names += [g["names"][g["name_off"][k]:g["name_off"][k + 1]].tobytes().decode() for k in range(st.n)]
+    assert names == [r["name"] for r in recs] and sum(sizes) == whole.n == len(recs)
+    assert len(sizes) == 2 and min(sizes) > 0.4 * window / per_record, sizes      # no quarter window at the end
+    st.close(); whole.close()
+
