@@ -5,7 +5,6 @@ flight (b_rows * 32*TBS * 2 B per chunk, summed over the resident sub-batch) and
 Parity at these configurations is covered by tests/test_gpu_parity.py; a sample item per row is re-checked against the
 oracle here when --check is given.
 usage: python tools/bench_configs.py [--quick] [--check]"""
-import gzip
 import json
 import os
 import sys

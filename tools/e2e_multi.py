@@ -5,7 +5,6 @@ import hashlib, os, re, sys, time
 from multiprocessing import get_context
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np
 import bench
 from npore_b200 import bamio, cfg
 
